@@ -1,0 +1,838 @@
+// ipt_capi.cu — the C ABI of include/ipt_b200.h: scene flattening, workspace management, the per-batch
+// kernel sequence of the wavefront pipeline, and the parity entry points.
+//
+// Host-side float work (light areas/normals/inverse matrices, mixture weights) follows the reference's
+// constructors in glm operation order (ipt_b200/host/glm_order.hpp) so the device consumes the same bits.
+#include "ipt_b200.h"
+
+#include "../host/glm_order.hpp"
+#include "ipt_lbvh.cuh"
+#include "ipt_trace.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace iptd;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                           \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess)                                                                                  \
+            return fail(IPT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                                          std::to_string(__LINE__) + ")");                                      \
+    } while (0)
+
+static bool check_eps_constants() {
+    // ipt_device.cuh: (double)x < 1e-6  <=>  x <= (float)1e-6
+    float f;
+    uint32_t bits = IPT_EPS6_BITS;
+    std::memcpy(&f, &bits, 4);
+    return f == (float)1e-6 && (double)f < 1e-6 && (double)std::nextafterf(f, 1.0f) > 1e-6;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// opaque handles
+// ---------------------------------------------------------------------------------------------------
+struct Workspace {
+    float4* ray_o = nullptr;
+    float4* ray_d = nullptr;
+    float4* hit_a = nullptr;
+    uint4* hit_b = nullptr;
+    float* pathval = nullptr;
+    size_t ray_cap = 0, hit_cap = 0, path_cap = 0;
+};
+
+struct ipt_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    DevScene dev{};
+    DevPrim* d_prims = nullptr;
+    DevLight* d_lights = nullptr;
+    DevMaterial* d_mats = nullptr;
+    LbvhDevice bvh{};
+    bool smallpt = false, mesh = false;
+    Workspace ws;
+    uint32_t* d_cnt = nullptr;
+    unsigned long long* d_stats = nullptr;
+    std::vector<cudaEvent_t> events;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    ipt_plane* host_plane = nullptr; // for ipt_render_host
+    float* pinned = nullptr;         // staging for ipt_render_host
+    size_t pinned_bytes = 0;
+    int grid_generate = 0, grid_extend = 0, grid_extend_last = 0, grid_shade = 0, grid_accumulate = 0;
+};
+
+struct ipt_plane {
+    ipt_scene* scene = nullptr;
+    uint32_t width = 0, height = 0;
+    float* sum = nullptr;
+    float* sumsq = nullptr;
+    uint32_t* count = nullptr;
+    bool owned = false;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// parity / utility kernels
+// ---------------------------------------------------------------------------------------------------
+template <bool SMALLPT, bool MESH>
+__global__ void __launch_bounds__(IPT_BLOCK) k_trace_batch(const __grid_constant__ DevScene S, const float* __restrict__ o,
+                                                           const float* __restrict__ d, size_t n, uint32_t* prim, float* t,
+                                                           uint32_t* light, float* lpos, uint32_t* outcome) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TraceCounters tc{0, 0};
+    Outcome oc = trace_scene<SMALLPT, MESH>(S, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tc);
+    if (prim) prim[i] = oc.surf.prim;
+    if (t) t[i] = oc.surf.prim == IPT_NO_HIT ? IPT_INF : oc.surf.t;
+    if (light) light[i] = oc.light;
+    if (lpos) { lpos[3 * i] = oc.light_pos.x; lpos[3 * i + 1] = oc.light_pos.y; lpos[3 * i + 2] = oc.light_pos.z; }
+    if (outcome) outcome[i] = oc.kind;
+}
+
+__global__ void k_camera_rays(const __grid_constant__ DevScene S, const float* __restrict__ xy, size_t n, float* o, float* d) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 oo, dd;
+    camera_ray(S.cam, xy[2 * i], xy[2 * i + 1], oo, dd);
+    o[3 * i] = oo.x; o[3 * i + 1] = oo.y; o[3 * i + 2] = oo.z;
+    d[3 * i] = dd.x; d[3 * i + 1] = dd.y; d[3 * i + 2] = dd.z;
+}
+
+__global__ void k_ddf_value(int kind, bool rotated, f3 to, const float* __restrict__ w, size_t n, float* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 a = mk3(w[3 * i], w[3 * i + 1], w[3 * i + 2]);
+    out[i] = base_value(kind, rotated ? dot3(to, a) : a.z);
+}
+__global__ void k_ddf_sample(int kind, bool rotated, f3 to, uint32_t k0, uint32_t k1, size_t n, float* w) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, 0xDDF0u, k0, k1);
+    f3 x = base_sample(kind, u01(r.y), u01(r.z));
+    if (rotated) x = rotate(make_basis(to), x);
+    w[3 * i] = x.x; w[3 * i + 1] = x.y; w[3 * i + 2] = x.z;
+}
+template <bool SMALLPT, bool MESH>
+__global__ void __launch_bounds__(IPT_BLOCK) k_mix_sample(const __grid_constant__ DevScene S, f3 o, f3 d, uint32_t k0, uint32_t k1, size_t n,
+                                                          float* w, float* mixv, float* sdfv, int* hit_flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TraceCounters tc{0, 0};
+    SurfHit sh = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
+    if (sh.prim == IPT_NO_HIT) { if (i == 0) *hit_flag = 0; return; }
+    if (i == 0) *hit_flag = 1;
+    if (i >= n) return;
+    f3 pos = xpoint(o, d, sh.t), normal;
+    uint32_t material;
+    surface_frame(S, sh.tri_pos != IPT_NO_HIT ? S.n_prims + sh.tri_pos : sh.prim, pos, normal, material);
+    DevMaterial m = material < IPT_INLINE_MATS ? S.mats[material] : S.mats_g[material];
+    Sdf sdf = make_sdf(m, normal, d);
+    Basis bn = make_basis(normal);
+    uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 1u, 0xDDF1u, k0, k1);
+    f3 x = mix_sample(S, sdf, bn, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+    w[3 * i] = x.x; w[3 * i + 1] = x.y; w[3 * i + 2] = x.z;
+    bool zero = x.x == 0.0f && x.y == 0.0f && x.z == 0.0f;
+    float sv = zero ? 0.0f : sdf_value(sdf, x);
+    sdfv[i] = sv;
+    mixv[i] = zero ? 0.0f : mix_value(S, sdf, pos, x, sv);
+}
+__global__ void k_light_ddf_value(const __grid_constant__ DevScene S, f3 pos, const float* __restrict__ w, size_t n, float* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 a = mk3(w[3 * i], w[3 * i + 1], w[3 * i + 2]);
+    Sdf dummy{};
+    // Lighting::distributionInPoint(pos)->value(w): the light weights before main.cpp:143 halves them
+    float v = mix_value(S, dummy, pos, a, 0.0f);
+    out[i] = S.n_lights ? v / (1.0f - S.sdf_weight) : 0.0f;
+}
+
+__global__ void k_plane_resolve(const float* __restrict__ sum, const uint32_t* __restrict__ count, size_t n, float* pixels) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pixels[i] = count[i] ? sum[i] / (float)count[i] : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scene flattening
+// ---------------------------------------------------------------------------------------------------
+static int flatten_lights(const ipt_scene_desc* d, std::vector<DevLight>& out, float& sdf_weight) {
+    namespace H = ipt_host;
+    uint32_t n = d->n_lights;
+    out.assign(n, DevLight{});
+    std::vector<float> w(n);
+    // CollectionLighting::distributionInPoint (src/CollectionLighting.cpp:12-21) through unite()'s union+simple
+    // branch (src/libddf/ddf.cpp:207-223): every earlier weight is rescaled each time a light is appended.
+    float acc_power = 0.0f;
+    for (uint32_t j = 0; j < n; ++j) {
+        float ka = acc_power, kb = d->lights[j].power;
+        float f = ka / (ka + kb);
+        for (uint32_t i = 0; i < j; ++i) w[i] *= f;
+        w[j] = kb / (ka + kb);
+        acc_power += kb;
+    }
+    // main.cpp:143 unite(light_ddf, 1, sdf, 1); with no lights unite() degenerates to the sdf alone (ddf.cpp:209-210)
+    if (n == 0) sdf_weight = 1.0f;
+    else {
+        float f = 1.0f / (1.0f + 1.0f);
+        for (uint32_t i = 0; i < n; ++i) w[i] *= f;
+        sdf_weight = 1.0f / (1.0f + 1.0f);
+    }
+    float acc = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const ipt_light& l = d->lights[i];
+        DevLight& o = out[i];
+        o.kind = l.kind;
+        o.power = l.power;
+        o.px = l.position[0]; o.py = l.position[1]; o.pz = l.position[2];
+        o.radius = l.radius;
+        o.xax = l.x_axis[0]; o.xay = l.x_axis[1]; o.xaz = l.x_axis[2];
+        o.yax = l.y_axis[0]; o.yay = l.y_axis[1]; o.yaz = l.y_axis[2];
+        if (l.kind == IPT_LIGHT_AREA_DIAMOND || l.kind == IPT_LIGHT_AREA_TRIANGLE) {
+            // AreaLight::AreaLight (src/lighting/lighting.cpp:79-90)
+            H::f3 xa = H::mk(l.x_axis), ya = H::mk(l.y_axis);
+            H::f3 cr = H::cross(xa, ya);
+            float full_area = H::length(cr);
+            o.area = l.kind == IPT_LIGHT_AREA_DIAMOND ? full_area : full_area / 2.0f;
+            H::f33 m;
+            m.c[0] = xa; m.c[1] = ya; m.c[2] = cr;
+            H::f33 inv = H::inverse(m);
+            o.i0x = inv.c[0].x; o.i0y = inv.c[1].x; o.i0z = inv.c[2].x;
+            o.i1x = inv.c[0].y; o.i1y = inv.c[1].y; o.i1z = inv.c[2].y;
+            H::f3 nn = H::normalize(cr);
+            o.nx = nn.x; o.ny = nn.y; o.nz = nn.z;
+            o.surface_power = l.power / o.area;
+        } else if (l.kind == IPT_LIGHT_SPHERE || l.kind == IPT_LIGHT_SPHERE_INVERTED) {
+            o.area = (float)(4.0 * M_PI * l.radius * l.radius); // lighting.h:51
+            o.surface_power = l.power / o.area;
+        } else if (l.kind == IPT_LIGHT_POINT) {
+            o.area = 0.0f;
+            o.surface_power = NAN; // lighting.cpp:204
+        } else {
+            return fail(IPT_ERR_INVALID, "unknown light kind");
+        }
+        o.weight = w[i];
+        acc += w[i];
+        o.cdf = acc;
+    }
+    return IPT_OK;
+}
+
+static int flatten_prims(const ipt_scene_desc* d, std::vector<DevPrim>& out, bool& smallpt) {
+    out.assign(d->n_prims, DevPrim{});
+    smallpt = false;
+    for (uint32_t i = 0; i < d->n_prims; ++i) {
+        const ipt_prim& p = d->prims[i];
+        DevPrim& o = out[i];
+        o.px = p.p[0]; o.py = p.p[1]; o.pz = p.p[2];
+        o.radius = p.radius;
+        o.kind = p.kind;
+        o.material = p.material;
+        o.curvature = p.curvature;
+        o.flags = p.flip_normal ? 8u : 0u;
+        if (p.material >= d->n_materials) return fail(IPT_ERR_INVALID, "primitive material index out of range");
+        if (p.kind == IPT_PRIM_BOX_PLANE) {
+            int axis = -1, nz = 0;
+            for (int a = 0; a < 3; ++a)
+                if (p.p[a] != 0.0f) { axis = a; ++nz; }
+            if (nz != 1 || std::fabs(p.p[axis]) != 1.0f)
+                return fail(IPT_ERR_INVALID, "box planes must be +-unit axis vectors (geometric_utils.cpp:8)");
+            o.flags |= (uint32_t)axis | (p.p[axis] < 0 ? 4u : 0u);
+        } else if (p.kind == IPT_PRIM_SPHERE_SMALLPT) {
+            smallpt = true;
+        } else if (p.kind != IPT_PRIM_SPHERE) {
+            return fail(IPT_ERR_INVALID, "unknown primitive kind");
+        }
+    }
+    return IPT_OK;
+}
+
+static void set_camera(DevScene& dev, const ipt_camera& c) {
+    std::memcpy(dev.cam.pos, c.position, 12);
+    std::memcpy(dev.cam.dir, c.direction, 12);
+    std::memcpy(dev.cam.right, c.right, 12);
+    std::memcpy(dev.cam.up, c.up, 12);
+}
+
+template <class K>
+static int occupancy_grid(K kernel, int sm_count, size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, IPT_BLOCK, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return sm_count * per_sm;
+}
+
+#define DISPATCH_SM(scene, CALL)                         \
+    do {                                                 \
+        if ((scene)->smallpt && (scene)->mesh) { CALL(true, true); }        \
+        else if ((scene)->smallpt) { CALL(true, false); }                   \
+        else if ((scene)->mesh) { CALL(false, true); }                      \
+        else { CALL(false, false); }                                        \
+    } while (0)
+
+static size_t stack_smem(const ipt_scene* s) { return s->mesh ? (size_t)IPT_STACK_SHORT * IPT_BLOCK * sizeof(uint32_t) : 0; }
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+
+extern "C" {
+
+int ipt_abi_version(void) { return IPT_B200_ABI_VERSION; }
+const char* ipt_last_error(void) { return g_last_error.c_str(); }
+int ipt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
+    if (!desc || !out) return fail(IPT_ERR_INVALID, "null argument");
+    if (!check_eps_constants()) return fail(IPT_ERR_INVALID, "float/double epsilon constants do not hold on this host");
+    if (ipt_device_count() <= device || device < 0) return fail(IPT_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (desc->n_materials == 0) return fail(IPT_ERR_INVALID, "scene has no materials");
+    if (desc->n_triangles && desc->triangle_material >= desc->n_materials) return fail(IPT_ERR_INVALID, "triangle material out of range");
+    if (desc->n_triangles >= 0x7FFFFFFFull) return fail(IPT_ERR_INVALID, "too many triangles");
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const ipt_material& m = desc->materials[i];
+        if (m.ddf == IPT_DDF_GLOSSY && !(m.exponent >= 3.0f && m.exponent == std::floor(m.exponent) && m.kd + m.ks > 0.0f))
+            return fail(IPT_ERR_INVALID, "glossy material needs an integer exponent >= 3 and kd+ks > 0");
+        if (m.ddf > IPT_DDF_GLOSSY) return fail(IPT_ERR_INVALID, "unknown ddf kind");
+    }
+    std::vector<DevPrim> prims;
+    std::vector<DevLight> lights;
+    bool smallpt = false;
+    float sdf_weight = 1.0f;
+    int rc = flatten_prims(desc, prims, smallpt);
+    if (rc) return rc;
+    rc = flatten_lights(desc, lights, sdf_weight);
+    if (rc) return rc;
+    std::vector<DevMaterial> mats(desc->n_materials);
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const ipt_material& m = desc->materials[i];
+        mats[i] = DevMaterial{};
+        mats[i].ddf = m.ddf;
+        mats[i].albedo = m.albedo;
+        if (m.ddf == IPT_DDF_GLOSSY) {
+            mats[i].wd = m.kd / (m.kd + m.ks);
+            mats[i].ws = m.ks / (m.kd + m.ks);
+        }
+        mats[i].exponent = m.exponent;
+    }
+
+    CUDA_TRY(cudaSetDevice(device));
+    ipt_scene* s = new ipt_scene();
+    s->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&s->ev_begin));
+    CUDA_TRY(cudaEventCreate(&s->ev_end));
+    DevScene& dv = s->dev;
+    std::memset(&dv, 0, sizeof dv);
+    dv.n_prims = desc->n_prims;
+    dv.n_lights = desc->n_lights;
+    dv.n_materials = desc->n_materials;
+    dv.has_smallpt = smallpt;
+    dv.sdf_weight = sdf_weight;
+    dv.prim_inline = desc->n_prims <= IPT_INLINE_PRIMS;
+    dv.light_inline = desc->n_lights <= IPT_INLINE_LIGHTS;
+    auto upload = [&](auto*& dptr, const auto& vec) -> cudaError_t {
+        size_t bytes = std::max<size_t>(vec.size(), 1) * sizeof(vec[0]);
+        cudaError_t e = cudaMalloc((void**)&dptr, bytes);
+        if (e != cudaSuccess) return e;
+        if (!vec.empty()) e = cudaMemcpy(dptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+        return e;
+    };
+    CUDA_TRY(upload(s->d_prims, prims));
+    CUDA_TRY(upload(s->d_lights, lights));
+    CUDA_TRY(upload(s->d_mats, mats));
+    dv.prims_g = s->d_prims;
+    dv.lights_g = s->d_lights;
+    dv.mats_g = s->d_mats;
+    for (uint32_t i = 0; i < desc->n_prims && i < IPT_INLINE_PRIMS; ++i) dv.prims[i] = prims[i];
+    for (uint32_t i = 0; i < desc->n_lights && i < IPT_INLINE_LIGHTS; ++i) dv.lights[i] = lights[i];
+    for (uint32_t i = 0; i < desc->n_materials && i < IPT_INLINE_MATS; ++i) dv.mats[i] = mats[i];
+    set_camera(dv, desc->camera);
+    s->smallpt = smallpt;
+    s->mesh = desc->n_triangles > 0;
+    if (s->mesh) {
+        std::string err;
+        if (lbvh_build(desc->triangles, (uint32_t)desc->n_triangles, s->stream, s->bvh, err) != 0) {
+            delete s;
+            return fail(IPT_ERR_CUDA, "LBVH build failed: " + err);
+        }
+        dv.n_tris = (uint32_t)desc->n_triangles;
+        dv.tri_material = desc->triangle_material;
+        dv.tris = s->bvh.tri_records;
+        dv.tri_id = s->bvh.sorted_ids;
+        dv.nodes = s->bvh.nodes;
+    }
+    CUDA_TRY(cudaMalloc((void**)&s->d_cnt, sizeof(uint32_t) * (2 * IPT_MAX_DEPTH + 2)));
+    CUDA_TRY(cudaMalloc((void**)&s->d_stats, sizeof(unsigned long long) * ST_COUNT));
+
+    size_t sm = stack_smem(s);
+    s->grid_generate = occupancy_grid(k_generate, s->sm_count, 0);
+    s->grid_shade = occupancy_grid(k_shade, s->sm_count, 0);
+    s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
+#define OCC(SP, MS)                                                                          \
+    s->grid_extend = occupancy_grid(k_extend<SP, MS, false>, s->sm_count, sm);               \
+    s->grid_extend_last = occupancy_grid(k_extend<SP, MS, true>, s->sm_count, sm)
+    DISPATCH_SM(s, OCC);
+#undef OCC
+    *out = s;
+    return IPT_OK;
+}
+
+static void free_workspace(Workspace& w) {
+    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.hit_a); cudaFree(w.hit_b); cudaFree(w.pathval);
+    w = Workspace();
+}
+
+int ipt_scene_destroy(ipt_scene* s) {
+    if (!s) return fail(IPT_ERR_INVALID, "null scene");
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    if (s->host_plane) ipt_plane_destroy(s->host_plane);
+    free_workspace(s->ws);
+    lbvh_free(s->bvh);
+    cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
+    if (s->pinned) cudaFreeHost(s->pinned);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    cudaEventDestroy(s->ev_begin); cudaEventDestroy(s->ev_end);
+    cudaStreamDestroy(s->stream);
+    delete s;
+    return IPT_OK;
+}
+
+int ipt_scene_set_camera(ipt_scene* s, const ipt_camera* camera) {
+    if (!s || !camera) return fail(IPT_ERR_INVALID, "null argument");
+    set_camera(s->dev, *camera);
+    return IPT_OK;
+}
+
+// ---- parity entries ----------------------------------------------------------------------------------
+int ipt_trace_batch(ipt_scene* s, const float* origins, const float* directions, size_t n, uint32_t* prim_id, float* t,
+                    uint32_t* light_id, float* light_pos, uint32_t* outcome) {
+    if (!s || !origins || !directions) return fail(IPT_ERR_INVALID, "null argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_o, d_d, d_t, d_lp;
+    DevBuf<uint32_t> d_prim, d_light, d_out;
+    CUDA_TRY(d_o.alloc(3 * n)); CUDA_TRY(d_d.alloc(3 * n)); CUDA_TRY(d_t.alloc(n)); CUDA_TRY(d_lp.alloc(3 * n));
+    CUDA_TRY(d_prim.alloc(n)); CUDA_TRY(d_light.alloc(n)); CUDA_TRY(d_out.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(d_o.p, origins, 12 * n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_d.p, directions, 12 * n, cudaMemcpyHostToDevice, s->stream));
+    unsigned blocks = (unsigned)((n + IPT_BLOCK - 1) / IPT_BLOCK);
+#define CALL(SP, MS) k_trace_batch<SP, MS><<<blocks, IPT_BLOCK, stack_smem(s), s->stream>>>(s->dev, d_o.p, d_d.p, n, d_prim.p, d_t.p, d_light.p, d_lp.p, d_out.p)
+    DISPATCH_SM(s, CALL);
+#undef CALL
+    CUDA_TRY(cudaGetLastError());
+    if (prim_id) CUDA_TRY(cudaMemcpyAsync(prim_id, d_prim.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    if (t) CUDA_TRY(cudaMemcpyAsync(t, d_t.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    if (light_id) CUDA_TRY(cudaMemcpyAsync(light_id, d_light.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    if (light_pos) CUDA_TRY(cudaMemcpyAsync(light_pos, d_lp.p, 12 * n, cudaMemcpyDeviceToHost, s->stream));
+    if (outcome) CUDA_TRY(cudaMemcpyAsync(outcome, d_out.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return IPT_OK;
+}
+
+int ipt_camera_rays(ipt_scene* s, const float* xy, size_t n, float* origins, float* directions) {
+    if (!s || !xy || !origins || !directions) return fail(IPT_ERR_INVALID, "null argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_xy, d_o, d_d;
+    CUDA_TRY(d_xy.alloc(2 * n)); CUDA_TRY(d_o.alloc(3 * n)); CUDA_TRY(d_d.alloc(3 * n));
+    CUDA_TRY(cudaMemcpyAsync(d_xy.p, xy, 8 * n, cudaMemcpyHostToDevice, s->stream));
+    k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->dev, d_xy.p, n, d_o.p, d_d.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(origins, d_o.p, 12 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(directions, d_d.p, 12 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return IPT_OK;
+}
+
+int ipt_ddf_value(ipt_scene* s, int kind, const float* to, const float* dirs, size_t n, float* out) {
+    if (!s || !dirs || !out || kind < 0) return fail(IPT_ERR_INVALID, "bad argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_w, d_out;
+    CUDA_TRY(d_w.alloc(3 * n)); CUDA_TRY(d_out.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(d_w.p, dirs, 12 * n, cudaMemcpyHostToDevice, s->stream));
+    f3 tv = to ? f3{to[0], to[1], to[2]} : f3{0, 0, 1};
+    k_ddf_value<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(kind, to != nullptr, tv, d_w.p, n, d_out.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return IPT_OK;
+}
+
+int ipt_ddf_sample(ipt_scene* s, int kind, const float* to, uint64_t seed, size_t n, float* dirs) {
+    if (!s || !dirs || kind < 0) return fail(IPT_ERR_INVALID, "bad argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_w;
+    CUDA_TRY(d_w.alloc(3 * n));
+    f3 tv = to ? f3{to[0], to[1], to[2]} : f3{0, 0, 1};
+    k_ddf_sample<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(kind, to != nullptr, tv, (uint32_t)seed, (uint32_t)(seed >> 32), n, d_w.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dirs, d_w.p, 12 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return IPT_OK;
+}
+
+int ipt_mix_sample(ipt_scene* s, const float origin[3], const float direction[3], uint64_t seed, size_t n, float* dirs,
+                   float* mix_value_out, float* sdf_value_out) {
+    if (!s || !origin || !direction || !dirs || !mix_value_out || !sdf_value_out) return fail(IPT_ERR_INVALID, "null argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_w, d_m, d_s;
+    DevBuf<int> d_flag;
+    CUDA_TRY(d_w.alloc(3 * n)); CUDA_TRY(d_m.alloc(n)); CUDA_TRY(d_s.alloc(n)); CUDA_TRY(d_flag.alloc(1));
+    f3 o{origin[0], origin[1], origin[2]}, d{direction[0], direction[1], direction[2]};
+    unsigned blocks = (unsigned)((n + IPT_BLOCK - 1) / IPT_BLOCK);
+#define CALL(SP, MS) k_mix_sample<SP, MS><<<blocks, IPT_BLOCK, stack_smem(s), s->stream>>>(s->dev, o, d, (uint32_t)seed, (uint32_t)(seed >> 32), n, d_w.p, d_m.p, d_s.p, d_flag.p)
+    DISPATCH_SM(s, CALL);
+#undef CALL
+    CUDA_TRY(cudaGetLastError());
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, d_flag.p, 4, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(dirs, d_w.p, 12 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(mix_value_out, d_m.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(sdf_value_out, d_s.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (!flag) return fail(IPT_ERR_INVALID, "the ray does not hit the geometry");
+    return IPT_OK;
+}
+
+int ipt_light_ddf_value(ipt_scene* s, const float pos[3], const float* dirs, size_t n, float* out) {
+    if (!s || !pos || !dirs || !out) return fail(IPT_ERR_INVALID, "null argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_w, d_out;
+    CUDA_TRY(d_w.alloc(3 * n)); CUDA_TRY(d_out.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(d_w.p, dirs, 12 * n, cudaMemcpyHostToDevice, s->stream));
+    k_light_ddf_value<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->dev, f3{pos[0], pos[1], pos[2]}, d_w.p, n, d_out.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return IPT_OK;
+}
+
+int ipt_bvh_export(ipt_scene* s, ipt_bvh_node* nodes, uint32_t* sorted_prims, uint64_t* morton, uint64_t* n_nodes) {
+    if (!s) return fail(IPT_ERR_INVALID, "null scene");
+    if (!s->mesh) return fail(IPT_ERR_INVALID, "scene has no triangle mesh");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    uint32_t n = s->bvh.n;
+    static_assert(sizeof(ipt_bvh_node) == sizeof(BvhNode), "ABI node layout");
+    if (n_nodes) *n_nodes = n > 1 ? n - 1 : 0;
+    if (nodes && n > 1) CUDA_TRY(cudaMemcpy(nodes, s->bvh.nodes, sizeof(BvhNode) * (n - 1), cudaMemcpyDeviceToHost));
+    if (sorted_prims) CUDA_TRY(cudaMemcpy(sorted_prims, s->bvh.sorted_ids, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    if (morton) CUDA_TRY(cudaMemcpy(morton, s->bvh.sorted_keys, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    return IPT_OK;
+}
+
+// ---- render plane ---------------------------------------------------------------------------------------
+int ipt_plane_create(ipt_scene* s, uint32_t width, uint32_t height, ipt_plane** out) {
+    if (!s || !out || !width || !height) return fail(IPT_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    ipt_plane* p = new ipt_plane();
+    p->scene = s; p->width = width; p->height = height; p->owned = true;
+    size_t n = (size_t)width * height;
+    CUDA_TRY(cudaMalloc((void**)&p->sum, 4 * n));
+    CUDA_TRY(cudaMalloc((void**)&p->sumsq, 4 * n));
+    CUDA_TRY(cudaMalloc((void**)&p->count, 4 * n));
+    *out = p;
+    return ipt_plane_clear(p);
+}
+int ipt_plane_wrap(ipt_scene* s, uint32_t width, uint32_t height, float* d_sum, float* d_sumsq, uint32_t* d_count, ipt_plane** out) {
+    if (!s || !out || !width || !height || !d_sum || !d_sumsq || !d_count) return fail(IPT_ERR_INVALID, "bad argument");
+    ipt_plane* p = new ipt_plane();
+    p->scene = s; p->width = width; p->height = height; p->owned = false;
+    p->sum = d_sum; p->sumsq = d_sumsq; p->count = d_count;
+    *out = p;
+    return IPT_OK;
+}
+int ipt_plane_clear(ipt_plane* p) {
+    if (!p) return fail(IPT_ERR_INVALID, "null plane");
+    CUDA_TRY(cudaSetDevice(p->scene->device));
+    size_t n = (size_t)p->width * p->height;
+    CUDA_TRY(cudaMemsetAsync(p->sum, 0, 4 * n, p->scene->stream));
+    CUDA_TRY(cudaMemsetAsync(p->sumsq, 0, 4 * n, p->scene->stream));
+    CUDA_TRY(cudaMemsetAsync(p->count, 0, 4 * n, p->scene->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->scene->stream));
+    return IPT_OK;
+}
+int ipt_plane_destroy(ipt_plane* p) {
+    if (!p) return fail(IPT_ERR_INVALID, "null plane");
+    if (p->owned) {
+        cudaSetDevice(p->scene->device);
+        cudaFree(p->sum); cudaFree(p->sumsq); cudaFree(p->count);
+    }
+    if (p->scene && p->scene->host_plane == p) p->scene->host_plane = nullptr;
+    delete p;
+    return IPT_OK;
+}
+int ipt_plane_download(ipt_plane* p, float* sum, float* sumsq, uint32_t* count) {
+    if (!p) return fail(IPT_ERR_INVALID, "null plane");
+    CUDA_TRY(cudaSetDevice(p->scene->device));
+    size_t n = (size_t)p->width * p->height;
+    cudaStream_t st = p->scene->stream;
+    if (sum) CUDA_TRY(cudaMemcpyAsync(sum, p->sum, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (sumsq) CUDA_TRY(cudaMemcpyAsync(sumsq, p->sumsq, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (count) CUDA_TRY(cudaMemcpyAsync(count, p->count, 4 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return IPT_OK;
+}
+int ipt_plane_upload(ipt_plane* p, const float* sum, const float* sumsq, const uint32_t* count) {
+    if (!p || !sum || !sumsq || !count) return fail(IPT_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(p->scene->device));
+    size_t n = (size_t)p->width * p->height;
+    cudaStream_t st = p->scene->stream;
+    CUDA_TRY(cudaMemcpyAsync(p->sum, sum, 4 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->sumsq, sumsq, 4 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->count, count, 4 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return IPT_OK;
+}
+int ipt_plane_device_ptrs(ipt_plane* p, float** d_sum, float** d_sumsq, uint32_t** d_count) {
+    if (!p) return fail(IPT_ERR_INVALID, "null plane");
+    if (d_sum) *d_sum = p->sum;
+    if (d_sumsq) *d_sumsq = p->sumsq;
+    if (d_count) *d_count = p->count;
+    return IPT_OK;
+}
+int ipt_plane_resolve(ipt_plane* p, float* pixels, uint64_t* pixel_counters, float* max_value) {
+    if (!p || !pixels) return fail(IPT_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(p->scene->device));
+    size_t n = (size_t)p->width * p->height;
+    DevBuf<float> d_pix;
+    CUDA_TRY(d_pix.alloc(n));
+    k_plane_resolve<<<(unsigned)((n + 255) / 256), 256, 0, p->scene->stream>>>(p->sum, p->count, n, d_pix.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(pixels, d_pix.p, 4 * n, cudaMemcpyDeviceToHost, p->scene->stream));
+    std::vector<uint32_t> cnt;
+    if (pixel_counters) {
+        cnt.resize(n);
+        CUDA_TRY(cudaMemcpyAsync(cnt.data(), p->count, 4 * n, cudaMemcpyDeviceToHost, p->scene->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->scene->stream));
+    if (pixel_counters) for (size_t i = 0; i < n; ++i) pixel_counters[i] = cnt[i];
+    if (max_value) {
+        float m = 0.0f; // GridRenderPlane::max_value starts at 0 (GridRenderPlane.h:12)
+        for (size_t i = 0; i < n; ++i) m = std::max(m, pixels[i]);
+        *max_value = m;
+    }
+    return IPT_OK;
+}
+
+// ---- the hot path ------------------------------------------------------------------------------------------
+void ipt_render_params_default(ipt_render_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->width = 640; p->height = 640; // main.cpp:189-190
+    p->depth_max = 4;                // main.cpp:95
+    p->schedule[0] = 16; p->schedule[1] = 8; p->schedule[2] = 4; p->schedule[3] = 2; // main.cpp:94,177 (n_rays/2)
+    p->seed = 0;
+    p->pass_begin = 0; p->pass_count = 1;
+    p->plane_mode = IPT_PLANE_GRID;
+}
+
+static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t path_cap) {
+    Workspace& w = s->ws;
+    if (w.ray_cap >= ray_cap && w.hit_cap >= hit_cap && w.path_cap >= path_cap) return IPT_OK;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    free_workspace(w);
+    CUDA_TRY(cudaMalloc((void**)&w.ray_o, 16 * ray_cap));
+    CUDA_TRY(cudaMalloc((void**)&w.ray_d, 16 * ray_cap));
+    CUDA_TRY(cudaMalloc((void**)&w.hit_a, 16 * std::max<size_t>(hit_cap, 1)));
+    CUDA_TRY(cudaMalloc((void**)&w.hit_b, 16 * std::max<size_t>(hit_cap, 1)));
+    CUDA_TRY(cudaMalloc((void**)&w.pathval, 4 * path_cap));
+    w.ray_cap = ray_cap; w.hit_cap = hit_cap; w.path_cap = path_cap;
+    return IPT_OK;
+}
+
+int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_render_stats* stats) {
+    if (!s || !plane || !p) return fail(IPT_ERR_INVALID, "null argument");
+    if (plane->scene != s) return fail(IPT_ERR_INVALID, "plane belongs to another scene");
+    if (!p->width || !p->height || plane->width != p->width || plane->height != p->height)
+        return fail(IPT_ERR_INVALID, "plane size does not match render params");
+    if (p->depth_max == 0 || p->depth_max > IPT_MAX_DEPTH) return fail(IPT_ERR_INVALID, "depth_max out of range");
+    if ((uint64_t)p->width * p->height > 0xFFFFFFFFull) return fail(IPT_ERR_INVALID, "frame too large");
+    uint32_t tx0 = p->tile_w ? p->tile_x0 : 0, ty0 = p->tile_w ? p->tile_y0 : 0;
+    uint32_t tw = p->tile_w ? p->tile_w : p->width, th = p->tile_w ? p->tile_h : p->height;
+    if (!tw || !th || tx0 + tw > p->width || ty0 + th > p->height) return fail(IPT_ERR_INVALID, "tile outside the frame");
+    if (p->plane_mode > IPT_PLANE_LINEAR) return fail(IPT_ERR_INVALID, "unknown plane mode");
+    CUDA_TRY(cudaSetDevice(s->device));
+
+    // widest tree level among traced depths -> bits for the node index inside the ray tag
+    uint64_t width_at[IPT_MAX_DEPTH];
+    uint64_t w = 1, max_ray_w = 1, max_hit_w = 1;
+    for (uint32_t d = 0; d < p->depth_max; ++d) {
+        width_at[d] = w;
+        max_ray_w = std::max(max_ray_w, w);
+        if (d + 1 < p->depth_max) max_hit_w = std::max(max_hit_w, w);
+        w *= p->schedule[d];
+        if (w > (1ull << 31)) return fail(IPT_ERR_UNSUPPORTED, "split schedule too wide (more than 2^31 nodes per tree level)");
+        if (w == 0 && d + 1 < p->depth_max) { /* schedule[d]==0: deeper levels never exist */
+            for (uint32_t e = d + 1; e < p->depth_max; ++e) width_at[e] = 0;
+            break;
+        }
+    }
+    uint32_t idx_bits = 0;
+    while ((1ull << idx_bits) < max_ray_w) ++idx_bits;
+    uint32_t slot_bits = 32 - idx_bits;
+    uint64_t total_paths = (uint64_t)tw * th * p->pass_count;
+    uint64_t batch = p->batch_paths ? p->batch_paths : (1u << 18);
+    batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
+    const uint64_t budget = 24ull << 30; // bytes of queue memory
+    while (batch > 1024 && batch * (max_ray_w + max_hit_w) * 32 > budget) batch >>= 1;
+    batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(total_paths, 1)));
+    int rc = ensure_workspace(s, batch * max_ray_w, batch * max_hit_w, batch);
+    if (rc) return rc;
+
+    RenderCtx C;
+    std::memset(&C, 0, sizeof C);
+    C.ray_o = s->ws.ray_o; C.ray_d = s->ws.ray_d; C.hit_a = s->ws.hit_a; C.hit_b = s->ws.hit_b; C.pathval = s->ws.pathval;
+    C.cnt = s->d_cnt; C.stats = s->d_stats;
+    C.sum = plane->sum; C.sumsq = plane->sumsq; C.count = plane->count;
+    C.width = p->width; C.height = p->height;
+    C.tile_x0 = tx0; C.tile_y0 = ty0; C.tile_w = tw; C.tile_h = th; C.tile_pixels = tw * th;
+    C.pass_begin = p->pass_begin;
+    C.slot_bits = slot_bits;
+    C.slot_mask = slot_bits >= 32 ? 0xFFFFFFFFu : ((1u << slot_bits) - 1u);
+    C.depth_max = p->depth_max;
+    std::memcpy(C.schedule, p->schedule, sizeof C.schedule);
+    C.k0 = (uint32_t)p->seed; C.k1 = (uint32_t)(p->seed >> 32);
+    C.plane_mode = p->plane_mode; C.flags = p->flags;
+
+    const bool timing = (p->flags & IPT_FLAG_TIME_KERNELS) != 0;
+    std::vector<int> ev_kind; // 0 generate 1 extend 2 shade 3 accumulate, one entry per bracketed launch
+    size_t ev_used = 0;
+    auto ev_next = [&]() -> cudaEvent_t {
+        if (ev_used == s->events.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            s->events.push_back(e);
+        }
+        return s->events[ev_used++];
+    };
+    uint32_t launches = 0;
+    CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, sizeof(unsigned long long) * ST_COUNT, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev_begin, s->stream));
+    size_t sm = stack_smem(s);
+    uint32_t batches = 0;
+    for (uint64_t g0 = 0; g0 < total_paths; g0 += batch, ++batches) {
+        C.g0 = g0;
+        C.batch = (uint32_t)std::min<uint64_t>(batch, total_paths - g0);
+        CUDA_TRY(cudaMemsetAsync(s->d_cnt, 0, sizeof(uint32_t) * (2 * IPT_MAX_DEPTH + 2), s->stream));
+#define TIMED(kind, LAUNCH)                                             \
+    do {                                                                \
+        if (timing) { cudaEventRecord(ev_next(), s->stream); }         \
+        LAUNCH;                                                         \
+        ++launches;                                                     \
+        if (timing) { cudaEventRecord(ev_next(), s->stream); ev_kind.push_back(kind); } \
+    } while (0)
+        int gg = std::min<int>(s->grid_generate, (int)((C.batch + IPT_BLOCK - 1) / IPT_BLOCK));
+        TIMED(0, (k_generate<<<gg, IPT_BLOCK, 0, s->stream>>>(s->dev, C)));
+        for (uint32_t d = 0; d < p->depth_max; ++d) {
+            if (width_at[d] == 0) break;
+            bool last = (d + 1 == p->depth_max) || p->schedule[d] == 0;
+            // never launch more warps than the level can have rays
+            uint64_t max_rays = (uint64_t)C.batch * width_at[d];
+            int cap_blocks = (int)std::min<uint64_t>((max_rays + IPT_BLOCK - 1) / IPT_BLOCK, 1u << 30);
+            if (last) {
+                int g = std::max(1, std::min(s->grid_extend_last, cap_blocks));
+#define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
+                DISPATCH_SM(s, CALL);
+#undef CALL
+                break;
+            }
+            int g = std::max(1, std::min(s->grid_extend, cap_blocks));
+#define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
+            DISPATCH_SM(s, CALL);
+#undef CALL
+            int gs = std::max(1, std::min(s->grid_shade, cap_blocks));
+            TIMED(2, (k_shade<<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+        }
+        TIMED(3, (k_accumulate<<<std::max(1, gg), IPT_BLOCK, 0, s->stream>>>(C)));
+#undef TIMED
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(s->ev_end, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaGetLastError());
+
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        unsigned long long h[ST_COUNT];
+        CUDA_TRY(cudaMemcpy(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        stats->paths = h[ST_PATHS];
+        for (int d = 0; d < IPT_MAX_DEPTH; ++d) {
+            stats->rays_at_depth[d] = h[ST_RAYS_AT_DEPTH + d];
+            stats->rays += h[ST_RAYS_AT_DEPTH + d];
+        }
+        stats->surface_hits = h[ST_SURFACE];
+        stats->light_hits = h[ST_LIGHT];
+        stats->misses = h[ST_MISS];
+        stats->failed_samples = h[ST_FAILED];
+        stats->zero_weight_pruned = h[ST_PRUNED];
+        stats->nonfinite_dropped = h[ST_DROPPED];
+        stats->bvh_nodes_visited = h[ST_NODES];
+        stats->triangles_tested = h[ST_TRIS];
+        stats->lights_tested = stats->rays * s->dev.n_lights;
+        stats->batches = batches;
+        stats->kernel_launches = launches;
+        CUDA_TRY(cudaEventElapsedTime(&stats->ms_total, s->ev_begin, s->ev_end));
+        if (timing) {
+            for (size_t k = 0; k < ev_kind.size(); ++k) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, s->events[2 * k], s->events[2 * k + 1]);
+                switch (ev_kind[k]) {
+                    case 0: stats->ms_generate += ms; break;
+                    case 1: stats->ms_extend += ms; ++stats->n_extend; break;
+                    case 2: stats->ms_shade += ms; ++stats->n_shade; break;
+                    default: stats->ms_accumulate += ms; break;
+                }
+            }
+        }
+        // ray record written + read (2 x 32 B) per ray, hit record written + read per QUEUED surface hit, pathval RMW
+        stats->queue_bytes = 64ull * stats->rays + 64ull * h[ST_QUEUED] + 8ull * stats->paths;
+    }
+    return IPT_OK;
+}
+
+int ipt_render_host(ipt_scene* s, const ipt_render_params* p, float* sum, float* sumsq, uint32_t* count, ipt_render_stats* stats) {
+    if (!s || !p || !sum) return fail(IPT_ERR_INVALID, "null argument");
+    if (s->host_plane && (s->host_plane->width != p->width || s->host_plane->height != p->height)) {
+        ipt_plane_destroy(s->host_plane);
+        s->host_plane = nullptr;
+    }
+    if (!s->host_plane) {
+        int rc = ipt_plane_create(s, p->width, p->height, &s->host_plane);
+        if (rc) return rc;
+    } else {
+        int rc = ipt_plane_clear(s->host_plane);
+        if (rc) return rc;
+    }
+    int rc = ipt_render(s, s->host_plane, p, stats);
+    if (rc) return rc;
+    return ipt_plane_download(s->host_plane, sum, sumsq, count);
+}
+
+} // extern "C"

@@ -1,0 +1,367 @@
+// ipt_kernels.cuh — the wavefront pipeline: generate -> [extend -> shade] x depth -> accumulate.
+//
+// It replaces the recursive per-pixel loop render_sample -> ray_power_recursive (src/main.cpp:98-223).
+// The estimator is linear in the leaf emissions (each surface hit divides by its child count and multiplies
+// by sdf/mix * albedo, main.cpp:172-181), so every ray simply carries the product of those factors
+// ("throughput") and a light hit adds throughput * emission to its path; no tree reduction is needed.
+//
+// Queues (SoA, one 128-bit load/store per field and thread, coalesced):
+//   ray  : float4 (origin.xyz, throughput)  float4 (direction.xyz, tag)             32 B
+//   hit  : float4 (position.xyz, throughput) uint4 (tag, prim, ray index, unused)   32 B
+//   tag  = path slot in the batch | node index within its tree level << slot_bits
+// Live-path compaction: a ray that misses or reaches a light writes nothing; survivors are appended with a
+// warp ballot + one atomicAdd per warp (warp-aggregated stream compaction).
+// All kernels are persistent grid-stride loops over a device-side element count, so no host round trip
+// separates the stages.
+#pragma once
+#include "ipt_shading.cuh"
+
+namespace iptd {
+
+enum StatSlot {
+    ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED,
+    ST_RAYS_AT_DEPTH = 16, // + depth
+    ST_COUNT = 16 + IPT_MAX_DEPTH
+};
+
+struct RenderCtx {
+    // queues
+    float4* ray_o;
+    float4* ray_d;
+    float4* hit_a;
+    uint4* hit_b;
+    float* pathval;
+    uint32_t* cnt;             // [2*d] rays at depth d, [2*d+1] surface hits at depth d
+    unsigned long long* stats; // StatSlot
+    // accumulators
+    float* sum;
+    float* sumsq;
+    uint32_t* count;
+    // frame / batch
+    uint32_t width, height;
+    uint32_t tile_x0, tile_y0, tile_w, tile_h, tile_pixels;
+    uint32_t pass_begin;
+    unsigned long long g0; // first global path index of the batch
+    uint32_t batch;        // paths in this batch
+    uint32_t slot_bits, slot_mask;
+    uint32_t depth_max;
+    uint32_t schedule[IPT_MAX_DEPTH];
+    uint32_t k0, k1; // Philox key
+    uint32_t plane_mode, flags;
+};
+
+__device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+
+// slot -> loop pixel and pass (render_sample's iy/ix loops, main.cpp:189-190)
+__device__ __forceinline__ void slot_to_pixel(const RenderCtx& C, uint32_t slot, uint32_t& ix, uint32_t& iy, uint32_t& pass) {
+    unsigned long long g = C.g0 + slot;
+    uint32_t p = (uint32_t)(g / C.tile_pixels);
+    uint32_t pl = (uint32_t)(g - (unsigned long long)p * C.tile_pixels);
+    uint32_t ty = pl / C.tile_w;
+    ix = C.tile_x0 + (pl - ty * C.tile_w);
+    iy = C.tile_y0 + ty;
+    pass = C.pass_begin + p;
+}
+
+// jittered sample position (main.cpp:192-198), exact float ops
+__device__ __forceinline__ void jitter_xy(const RenderCtx& C, uint32_t ix, uint32_t iy, uint32_t pass, float& x, float& y) {
+    uint4 r = philox4x32_10(iy * C.width + ix, pass, 0u, 0u, C.k0, C.k1);
+    x = xdiv(xadd((float)ix, u01(r.x)), (float)C.width);
+    y = xdiv(xadd((float)iy, u01(r.y)), (float)C.height);
+    if (x == 1.0f) x = __uint_as_float(0x3F7FFFFFu); // nextafter(1.0f, 0.0f)
+    if (y == 1.0f) y = __uint_as_float(0x3F7FFFFFu);
+}
+
+// SimpleCamera::sampleRay (src/SimpleCamera.cpp:15-21), exact
+__device__ __forceinline__ void camera_ray(const DevCamera& cam, float x, float y, f3& o, f3& d) {
+    x = xsub(x, 0.5f);
+    y = xsub(y, 0.5f);
+    f3 ray = xadd3(xadd3(xscale3(ld3(cam.right), x), xscale3(ld3(cam.up), y)), ld3(cam.dir));
+    o = ld3(cam.pos);
+    d = xnormalize3(ray);
+}
+
+// K1 generate: one thread per path of the batch.
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < C.batch; slot += stride) {
+        uint32_t ix, iy, pass;
+        slot_to_pixel(C, slot, ix, iy, pass);
+        float x, y;
+        jitter_xy(C, ix, iy, pass, x, y);
+        f3 o, d;
+        camera_ray(S.cam, x, y, o, d);
+        C.ray_o[slot] = make_float4(o.x, o.y, o.z, 1.0f);
+        C.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
+        C.pathval[slot] = 0.0f;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) C.cnt[0] = C.batch;
+}
+
+// ---- closest hit over the whole scene (Geometry::traceRay) ------------------------------------------
+struct TraceCounters {
+    uint32_t nodes, tris;
+};
+
+template <bool SMALLPT, bool MESH>
+__device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc);
+
+// ---- nearest light (CollectionLighting::traceRayToLight, src/CollectionLighting.cpp:23-34) -----------
+template <class LightAt>
+__device__ __forceinline__ bool trace_lights(uint32_t n, LightAt at, f3 o, f3 d, uint32_t& which, f3& lpos) {
+    bool any = false;
+    float best_len = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        LightHit e = light_trace(at(i), o, d);
+        if (!e.hit) continue;
+        float len = xlength3(xsub3(e.position, o));
+        if (!any || best_len > len) {
+            any = true;
+            best_len = len;
+            which = i;
+            lpos = e.position;
+        }
+    }
+    return any;
+}
+
+struct Outcome {
+    uint32_t kind; // 0 miss, 1 surface, 2 light
+    SurfHit surf;
+    uint32_t light;
+    f3 light_pos;
+};
+
+// Geometry::traceRay + Lighting::traceRayToLight + the decision of main.cpp:111-128
+template <bool SMALLPT, bool MESH>
+__device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
+    Outcome r;
+    r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
+    r.light = IPT_NO_HIT;
+    r.light_pos = mk3(0, 0, 0);
+    bool lh;
+    if (S.light_inline) lh = trace_lights(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights[i]; }, o, d, r.light, r.light_pos);
+    else lh = trace_lights(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights_g[i]; }, o, d, r.light, r.light_pos);
+    bool sh = r.surf.prim != IPT_NO_HIT;
+    r.kind = 0;
+    if (lh) {
+        bool light_wins = !sh;
+        if (sh) {
+            f3 sp = xpoint(o, d, r.surf.t);
+            light_wins = xlength3(xsub3(sp, o)) > xlength3(xsub3(r.light_pos, o));
+        }
+        if (light_wins) { r.kind = 2; return r; }
+    }
+    if (sh) r.kind = 1;
+    return r;
+}
+
+__device__ __forceinline__ void flush_stat(unsigned long long* stats, int slot, uint32_t v) {
+    // warp reduce, then one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats[slot], (unsigned long long)v);
+}
+
+// K2 extend: one thread per ray of depth `depth`. Light hits are accumulated here (the emission is the leaf
+// of the estimator tree); surface hits are compacted into the hit queue unless this is the last traced depth.
+template <bool SMALLPT, bool MESH, bool LAST>
+__global__ void __launch_bounds__(256) k_extend(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+    const uint32_t n = C.cnt[2 * depth];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t n_surface = 0, n_light = 0, n_miss = 0;
+    TraceCounters tc{0, 0};
+    for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
+        uint32_t i = base + lane;
+        bool active = i < n;
+        bool emit = false;
+        float4 ro, rd;
+        Outcome oc;
+        if (active) {
+            ro = C.ray_o[i];
+            rd = C.ray_d[i];
+            f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
+            oc = trace_scene<SMALLPT, MESH>(S, o, d, tc);
+            if (oc.kind == 2) {
+                ++n_light;
+                float power = S.light_inline ? S.lights[oc.light].surface_power : S.lights_g[oc.light].surface_power;
+                if (!isfinite(power)) power = 1.0f; // main.cpp:123 point-light hack
+                uint32_t slot = __float_as_uint(rd.w) & C.slot_mask;
+                atomicAdd(&C.pathval[slot], ro.w * power);
+            } else if (oc.kind == 1) {
+                ++n_surface;
+                emit = !LAST;
+            } else {
+                ++n_miss;
+            }
+        }
+        if (!LAST) {
+            uint32_t ballot = __ballot_sync(0xffffffffu, emit);
+            if (ballot) {
+                uint32_t basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&C.cnt[2 * depth + 1], __popc(ballot));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (emit) {
+                    uint32_t j = basepos + __popc(ballot & ((1u << lane) - 1u));
+                    f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), oc.surf.t);
+                    C.hit_a[j] = make_float4(p.x, p.y, p.z, ro.w);
+                    uint32_t iprim = oc.surf.tri_pos != IPT_NO_HIT ? S.n_prims + oc.surf.tri_pos : oc.surf.prim;
+                    C.hit_b[j] = make_uint4(__float_as_uint(rd.w), iprim, i, 0u);
+                }
+            }
+        }
+    }
+    flush_stat(C.stats, ST_SURFACE, n_surface);
+    flush_stat(C.stats, ST_LIGHT, n_light);
+    flush_stat(C.stats, ST_MISS, n_miss);
+    if (MESH) {
+        flush_stat(C.stats, ST_NODES, tc.nodes);
+        flush_stat(C.stats, ST_TRIS, tc.tris);
+    }
+}
+
+// geometric normal + material of a hit primitive (GeometrySphereInBox.cpp:43-56 and the other geometries)
+__device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, f3 pos, f3& normal, uint32_t& material) {
+    if (prim >= S.n_prims) {
+        uint32_t k = prim - S.n_prims; // sorted triangle position
+        float4 a = __ldg(&S.tris[3 * (size_t)k]);
+        float4 b = __ldg(&S.tris[3 * (size_t)k + 1]);
+        normal = mk3(a.w, b.x, b.y);
+        material = S.tri_material;
+        return;
+    }
+    DevPrim p = S.prim_inline ? S.prims[prim] : S.prims_g[prim];
+    material = p.material;
+    if (p.kind == IPT_PRIM_BOX_PLANE) {
+        normal = mk3(-p.px, -p.py, -p.pz);
+    } else {
+        f3 nn = xnormalize3(xsub3(pos, mk3(p.px, p.py, p.pz)));
+        normal = (p.flags & 8u) ? neg3(nn) : nn;
+    }
+}
+
+// K3 shade: one thread per surface hit; spawns schedule[depth] children from the 1:1 mixture of the light DDF
+// and the surface DDF (main.cpp:142-177) and appends the survivors to the ray queue of depth+1.
+__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+    const uint32_t n = C.cnt[2 * depth + 1];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_children = C.schedule[depth];
+    const float inv_n = 1.0f / (float)n_children;
+    uint32_t n_failed = 0, n_pruned = 0, n_dropped = 0;
+    uint32_t* out_count = &C.cnt[2 * (depth + 1)];
+    for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
+        uint32_t i = base + lane;
+        bool active = i < n;
+        f3 pos = mk3(0, 0, 0);
+        float thr = 0.0f;
+        uint32_t tag = 0, node = 0, pixel = 0, pass = 0;
+        Sdf sdf;
+        Basis bn;
+        float albedo = 1.0f;
+        if (active) {
+            float4 a = C.hit_a[i];
+            uint4 b = C.hit_b[i];
+            pos = mk3(a.x, a.y, a.z);
+            thr = a.w;
+            tag = b.x;
+            node = tag >> C.slot_bits;
+            if (C.slot_bits == 32) node = 0;
+            uint32_t ix, iy;
+            slot_to_pixel(C, tag & C.slot_mask, ix, iy, pass);
+            pixel = iy * C.width + ix;
+            f3 normal;
+            uint32_t material;
+            surface_frame(S, b.y, pos, normal, material);
+            DevMaterial m = material < IPT_INLINE_MATS ? S.mats[material] : S.mats_g[material];
+            albedo = m.albedo;
+            f3 din = mk3(0, 0, 0);
+            if (m.ddf == IPT_DDF_GLOSSY) {
+                float4 rd = C.ray_d[b.z]; // the incoming direction is only needed for the glossy lobe
+                din = mk3(rd.x, rd.y, rd.z);
+            }
+            sdf = make_sdf(m, normal, din);
+            bn = make_basis(normal);
+        }
+        for (uint32_t c = 0; c < n_children; ++c) {
+            bool emit = false;
+            f3 w = mk3(0, 0, 0);
+            float wgt = 0.0f;
+            uint32_t child = node * n_children + c;
+            if (active) {
+                uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
+                w = mix_sample(S, sdf, bn, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
+                    ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
+                } else {
+                    float sv = sdf_value(sdf, w);
+                    float mv = mix_value(S, sdf, pos, w, sv);
+                    float mult = sv / mv;
+                    wgt = thr * (mult * albedo) * inv_n;
+                    if (!isfinite(wgt)) ++n_dropped;
+                    else if (wgt == 0.0f && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
+                    else emit = true;
+                }
+            }
+            uint32_t ballot = __ballot_sync(0xffffffffu, emit);
+            if (ballot) {
+                uint32_t basepos = 0;
+                if (lane == 0) basepos = atomicAdd(out_count, __popc(ballot));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (emit) {
+                    uint32_t j = basepos + __popc(ballot & ((1u << lane) - 1u));
+                    uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
+                    C.ray_o[j] = make_float4(pos.x, pos.y, pos.z, wgt);
+                    C.ray_d[j] = make_float4(w.x, w.y, w.z, __uint_as_float(ctag));
+                }
+            }
+        }
+    }
+    flush_stat(C.stats, ST_FAILED, n_failed);
+    flush_stat(C.stats, ST_PRUNED, n_pruned);
+    flush_stat(C.stats, ST_DROPPED, n_dropped);
+}
+
+// accumulator cell of a sample: GridRenderPlane::addRay (src/GridRenderPlane.cpp:66-67), Gui::addRay (gui.cpp:168-172)
+__device__ __forceinline__ uint32_t plane_cell(const RenderCtx& C, float x, float y, uint32_t ix, uint32_t iy) {
+    if (C.plane_mode == IPT_PLANE_LINEAR) return iy * C.width + ix;
+    float W = (float)C.width, H = (float)C.height;
+    int xi = (int)xmul(x, W); // size_t xi = x*width (truncation)
+    int yi;
+    if (C.plane_mode == IPT_PLANE_GRID) yi = (int)xsub(xsub(H, xmul(y, H)), 1.0f); // height - y*height - 1; (-1,0) truncates to 0
+    else yi = (int)xsub(H, xmul(y, H));
+    xi = min(max(xi, 0), (int)C.width - 1); // the reference would write out of bounds; unreachable for x,y in [0,1)
+    yi = min(max(yi, 0), (int)C.height - 1);
+    return (uint32_t)yi * C.width + (uint32_t)xi;
+}
+
+// K6 accumulate: one thread per path; RenderPlane::addRay for the path's value (main.cpp:213-216).
+__global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ RenderCtx C) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t dropped = 0;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < C.batch; slot += stride) {
+        float v = C.pathval[slot];
+        if (!isfinite(v)) { v = 0.0f; ++dropped; }
+        v = v >= 0.0f ? v : 0.0f;
+        uint32_t ix, iy, pass;
+        slot_to_pixel(C, slot, ix, iy, pass);
+        float x, y;
+        jitter_xy(C, ix, iy, pass, x, y);
+        uint32_t cell = plane_cell(C, x, y, ix, iy);
+        atomicAdd(&C.sum[cell], v);
+        atomicAdd(&C.sumsq[cell], v * v);
+        atomicAdd(&C.count[cell], 1u);
+    }
+    flush_stat(C.stats, ST_DROPPED, dropped);
+    // fold this batch's per-depth ray counts into the running statistics
+    if (blockIdx.x == 0 && threadIdx.x < IPT_MAX_DEPTH) {
+        uint32_t r = C.cnt[2 * threadIdx.x], h = C.cnt[2 * threadIdx.x + 1];
+        if (r) atomicAdd(&C.stats[ST_RAYS_AT_DEPTH + threadIdx.x], (unsigned long long)r);
+        if (h) atomicAdd(&C.stats[ST_QUEUED], (unsigned long long)h);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&C.stats[ST_PATHS], (unsigned long long)C.batch);
+}
+
+} // namespace iptd

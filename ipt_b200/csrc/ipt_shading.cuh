@@ -1,0 +1,185 @@
+// ipt_shading.cuh — DDF sampling / evaluation on the device (libddf + lighting DDFs of the reference).
+//
+// Everything downstream of a random number can only match the reference statistically (drand48 vs Philox,
+// SURVEY.md S6), so this file is free to use algebraically equivalent, cheaper forms:
+//   * RotateDdf's matrix (glm::rotate by acos(n.z) about z x n, ddf_detail.h:72-85) is built from
+//     c = n.z, s = |z x n| without any trigonometry; it is the same rotation.
+//   * TransformDdf::value(w) = origin.value(R^-1 w) only needs (R^-1 w).z = dot(R*z, w) = dot(axis_to, w).
+//   * sin(acos(x)) = sqrt(1 - x*x).
+// The intersection calls inside the light pdf stay on the exact routines of ipt_device.cuh.
+#pragma once
+#include "ipt_device.cuh"
+
+namespace iptd {
+
+#define IPT_PI_F 3.14159265358979323846f
+
+struct Basis { // columns of RotateDdf::transformation; c2 == the axis rotated to
+    f3 c0, c1, c2;
+};
+
+// RotateDdf::RotateDdf (src/libddf/ddf_detail.h:72-85)
+__device__ __forceinline__ Basis make_basis(f3 to) {
+    float c = to.z;
+    float axx = -to.y, axy = to.x; // cross((0,0,1), to) = (-to.y, to.x, 0)
+    float len2 = axx * axx + axy * axy;
+    float s = sqrtf(len2);
+    float ax, ay;
+    if (s < 1e-6f) { ax = 1.0f; ay = 0.0f; } // ddf_detail.h:77-78 degenerate axis -> (1,0,0)
+    else { float inv = 1.0f / s; ax = axx * inv; ay = axy * inv; }
+    // with the degenerate axis the angle is still acos(c): c = +-1, sin = sqrt(1-c*c)
+    float sn = sqrtf(fmaxf(0.0f, 1.0f - c * c));
+    float tx = (1.0f - c) * ax, ty = (1.0f - c) * ay;
+    Basis b;
+    b.c0 = mk3(c + tx * ax, tx * ay, -sn * ay);
+    b.c1 = mk3(ty * ax, c + ty * ay, sn * ax);
+    b.c2 = mk3(sn * ay, -sn * ax, c);
+    return b;
+}
+__device__ __forceinline__ f3 rotate(const Basis& b, f3 x) {
+    return mk3(b.c0.x * x.x + b.c1.x * x.y + b.c2.x * x.z, b.c0.y * x.x + b.c1.y * x.y + b.c2.y * x.z,
+               b.c0.z * x.x + b.c1.z * x.y + b.c2.z * x.z);
+}
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// Base DDFs in their own frame. kind: 0 Spherical (ddf.cpp:58-72), 1 UpperHalf (:74-89), 2 Cosine (:91-108),
+// >=3 PowerCosine(kind) (extension, oracle/ref_driver.cpp).
+__device__ __forceinline__ f3 base_sample(int kind, float u1, float u2) {
+    float zc;
+    if (kind == 0) zc = u1 * 2.0f - 1.0f;
+    else if (kind == 1) zc = u1;
+    else if (kind == 2) zc = sqrtf(u1);
+    else zc = powf(u1, 1.0f / ((float)kind + 1.0f));
+    float r = sqrtf(fmaxf(0.0f, 1.0f - zc * zc));
+    float sp, cp;
+    sincospif(2.0f * u2, &sp, &cp);
+    return mk3(r * cp, r * sp, zc);
+}
+__device__ __forceinline__ float base_value(int kind, float z) {
+    if (kind == 0) return 0.25f / IPT_PI_F;
+    if (z < 0.0f) return 0.0f;
+    if (kind == 1) return 0.5f / IPT_PI_F;
+    if (kind == 2) return z / IPT_PI_F;
+    return ((float)kind + 1.0f) * powf(z, (float)kind) / (2.0f * IPT_PI_F);
+}
+
+// The surface DDF of a hit: RotateDdf(CosineDdf, normal) or the glossy extension.
+struct Sdf {
+    uint32_t ddf;
+    f3 normal, refl;
+    float wd, ws;
+    int exponent;
+};
+__device__ __forceinline__ f3 reflect3(f3 I, f3 N) { // glm::reflect: I - N*dot(N,I)*2
+    float k = 2.0f * dot3(N, I);
+    return mk3(I.x - N.x * k, I.y - N.y * k, I.z - N.z * k);
+}
+__device__ __forceinline__ Sdf make_sdf(const DevMaterial& m, f3 normal, f3 dir_in) {
+    Sdf s;
+    s.ddf = m.ddf;
+    s.normal = normal;
+    s.wd = m.wd; s.ws = m.ws;
+    s.exponent = (int)m.exponent;
+    s.refl = m.ddf == IPT_DDF_GLOSSY ? reflect3(dir_in, normal) : normal;
+    return s;
+}
+__device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
+    float cn = dot3(s.normal, w);
+    if (s.ddf == IPT_DDF_COSINE) return base_value(2, cn);
+    if (cn < 0.0f) return 0.0f;
+    return s.wd * base_value(2, cn) + s.ws * base_value(s.exponent, dot3(s.refl, w));
+}
+// zero vector == failed sample. ul is the lobe-selection draw (ROLE_LOBE in the oracle).
+__device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, float u1, float u2, float ul) {
+    if (s.ddf == IPT_DDF_COSINE) return rotate(bn, base_sample(2, u1, u2));
+    f3 w;
+    if (ul < s.wd) w = rotate(bn, base_sample(2, u1, u2));
+    else w = rotate(make_basis(s.refl), base_sample(s.exponent, u1, u2));
+    if (dot3(s.normal, w) < 0.0f) return mk3(0, 0, 0);
+    return w;
+}
+
+// DdfFromLight::value (src/lighting/lighting.cpp:61-73)
+__device__ __forceinline__ float light_pdf(const DevLight& L, f3 pos, f3 w) {
+    LightHit h = light_trace(L, pos, w);
+    if (!h.hit) return 0.0f;
+    f3 dp = mk3(h.position.x - pos.x, h.position.y - pos.y, h.position.z - pos.z);
+    float decay = dot3(dp, dp);
+    float inv = rsqrtf(decay);
+    float cosinus = -(h.normal.x * dp.x + h.normal.y * dp.y + h.normal.z * dp.z) * inv;
+    if (cosinus < 0.0f) return 0.0f;
+    return decay / cosinus / L.area;
+}
+
+// DdfFromLight::sample (src/lighting/lighting.cpp:50-59) over Light::sample (lighting.cpp:93-104, 172-207)
+__device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float u1, float u2) {
+    f3 p, n;
+    if (L.kind <= IPT_LIGHT_AREA_TRIANGLE) {
+        float v2 = L.kind == IPT_LIGHT_AREA_TRIANGLE ? u2 * (1.0f - u1) : u2;
+        p = mk3(L.xax * u1 + L.yax * v2 + L.px, L.xay * u1 + L.yay * v2 + L.py, L.xaz * u1 + L.yaz * v2 + L.pz);
+        n = mk3(L.nx, L.ny, L.nz);
+    } else {
+        float z = u1 * 2.0f - 1.0f;
+        float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+        float sp, cp;
+        sincospif(2.0f * u2, &sp, &cp);
+        f3 unit = mk3(r * cp, r * sp, z);
+        if (L.kind == IPT_LIGHT_POINT) {
+            p = mk3(L.px, L.py, L.pz);
+            n = unit;
+        } else {
+            p = mk3(unit.x * L.radius + L.px, unit.y * L.radius + L.py, unit.z * L.radius + L.pz);
+            n = L.kind == IPT_LIGHT_SPHERE_INVERTED ? neg3(unit) : unit;
+        }
+    }
+    f3 dp = mk3(p.x - pos.x, p.y - pos.y, p.z - pos.z);
+    float inv = rsqrtf(dot3(dp, dp));
+    f3 dir = mk3(dp.x * inv, dp.y * inv, dp.z * inv);
+    float cosinus = -dot3(n, dir);
+    if (cosinus < 1e-5f) return mk3(0, 0, 0); // facing back: failed sample
+    return dir;
+}
+
+template <class LightAt>
+__device__ __forceinline__ float lights_pdf(uint32_t n, LightAt at, f3 pos, f3 w) {
+    float res = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const DevLight& L = at(i);
+        res += L.weight * light_pdf(L, pos, w);
+    }
+    return res;
+}
+
+// UnionDdf::value over [lights..., sdf] (src/libddf/ddf.cpp:156-162) with the weights of main.cpp:143
+__device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3 pos, f3 w, float sdf_val) {
+    float lp;
+    if (S.light_inline) lp = lights_pdf(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights[i]; }, pos, w);
+    else lp = lights_pdf(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights_g[i]; }, pos, w);
+    return lp + S.sdf_weight * sdf_val;
+}
+
+// UnionDdf::sample (src/libddf/ddf.cpp:138-154): scan the running float sum of weights with one draw.
+// r >= total (float rounding; uninitialised result in the reference) is a failed sample.
+__device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, f3 pos, float us, float u1, float u2, float ul) {
+    float acc = 0.0f;
+    if (S.light_inline) {
+        for (uint32_t i = 0; i < S.n_lights; ++i) {
+            acc = S.lights[i].cdf;
+            if (us < acc) return light_sample_dir(S.lights[i], pos, u1, u2);
+        }
+    } else if (S.n_lights) {
+        // first i with us < cdf[i]; cdf is non-decreasing, so a binary search finds what the linear scan finds
+        uint32_t lo = 0, hi = S.n_lights;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (us < S.lights_g[mid].cdf) hi = mid; else lo = mid + 1;
+        }
+        if (lo < S.n_lights) return light_sample_dir(S.lights_g[lo], pos, u1, u2);
+        acc = S.lights_g[S.n_lights - 1].cdf;
+    }
+    acc += S.sdf_weight;
+    if (us < acc) return sdf_sample(sdf, bn, u1, u2, ul);
+    return mk3(0, 0, 0);
+}
+
+} // namespace iptd
