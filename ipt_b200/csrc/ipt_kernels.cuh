@@ -7,7 +7,7 @@
 //
 // Queues (SoA, one 128-bit load/store per field and thread, coalesced):
 //   ray  : float4 (origin.xyz, throughput)  float4 (direction.xyz, tag)             32 B
-//   hit  : float4 (position.xyz, throughput) uint4 (tag, prim, ray index, unused)   32 B
+//   hit  : float4 (position.xyz, throughput) uint4 (tag, prim, octahedral incoming direction) 32 B
 //   tag  = path slot in the batch | node index within its tree level << slot_bits
 // Live-path compaction: a ray that misses or reaches a light writes nothing; survivors are appended with a
 // warp ballot + one atomicAdd per warp (warp-aggregated stream compaction).
@@ -15,6 +15,7 @@
 // separates the stages.
 #pragma once
 #include "ipt_shading.cuh"
+#include <cstdio>
 
 namespace iptd {
 
@@ -51,6 +52,30 @@ struct RenderCtx {
 };
 
 __device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+
+// Octahedral map of a unit vector to two floats (full float precision, ~1e-7): lets the 32-byte hit record carry
+// the incoming direction, which only the glossy lobe (reflect(d, n)) needs. The parent ray record cannot be re-read
+// at shading time: the shade kernel is already overwriting the ray queue with the next depth.
+__device__ __forceinline__ float2 oct_encode(f3 d) {
+    float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+    float px = d.x * inv, py = d.y * inv;
+    if (d.z < 0.0f) {
+        float tx = (1.0f - fabsf(py)) * copysignf(1.0f, px);
+        py = (1.0f - fabsf(px)) * copysignf(1.0f, py);
+        px = tx;
+    }
+    return make_float2(px, py);
+}
+__device__ __forceinline__ f3 oct_decode(float ex, float ey) {
+    float z = 1.0f - fabsf(ex) - fabsf(ey);
+    float x = ex, y = ey;
+    if (z < 0.0f) {
+        x = (1.0f - fabsf(ey)) * copysignf(1.0f, ex);
+        y = (1.0f - fabsf(ex)) * copysignf(1.0f, ey);
+    }
+    float inv = rsqrtf(x * x + y * y + z * z);
+    return mk3(x * inv, y * inv, z * inv);
+}
 
 // slot -> loop pixel and pass (render_sample's iy/ix loops, main.cpp:189-190)
 __device__ __forceinline__ void slot_to_pixel(const RenderCtx& C, uint32_t slot, uint32_t& ix, uint32_t& iy, uint32_t& pass) {
@@ -183,6 +208,9 @@ __global__ void __launch_bounds__(256) k_extend(const __grid_constant__ DevScene
             rd = C.ray_d[i];
             f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
             oc = trace_scene<SMALLPT, MESH>(S, o, d, tc);
+            if (C.flags & 4u)
+                printf("GPU extend d=%u node=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) thr=%.9g kind=%u prim=%u t=%.9g\n", depth,
+                       C.slot_bits == 32 ? 0u : (__float_as_uint(rd.w) >> C.slot_bits), o.x, o.y, o.z, d.x, d.y, d.z, ro.w, oc.kind, oc.surf.prim, oc.surf.t);
             if (oc.kind == 2) {
                 ++n_light;
                 float power = S.light_inline ? S.lights[oc.light].surface_power : S.lights_g[oc.light].surface_power;
@@ -207,7 +235,8 @@ __global__ void __launch_bounds__(256) k_extend(const __grid_constant__ DevScene
                     f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), oc.surf.t);
                     C.hit_a[j] = make_float4(p.x, p.y, p.z, ro.w);
                     uint32_t iprim = oc.surf.tri_pos != IPT_NO_HIT ? S.n_prims + oc.surf.tri_pos : oc.surf.prim;
-                    C.hit_b[j] = make_uint4(__float_as_uint(rd.w), iprim, i, 0u);
+                    float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
+                    C.hit_b[j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
                 }
             }
         }
@@ -278,10 +307,7 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DevScene 
             DevMaterial m = material < IPT_INLINE_MATS ? S.mats[material] : S.mats_g[material];
             albedo = m.albedo;
             f3 din = mk3(0, 0, 0);
-            if (m.ddf == IPT_DDF_GLOSSY) {
-                float4 rd = C.ray_d[b.z]; // the incoming direction is only needed for the glossy lobe
-                din = mk3(rd.x, rd.y, rd.z);
-            }
+            if (m.ddf == IPT_DDF_GLOSSY) din = oct_decode(__uint_as_float(b.z), __uint_as_float(b.w)); // only the glossy lobe needs it
             sdf = make_sdf(m, normal, din);
             bn = make_basis(normal);
         }
@@ -294,12 +320,15 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DevScene 
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
                 w = mix_sample(S, sdf, bn, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
+                    if (C.flags & 4u) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
                 } else {
                     float sv = sdf_value(sdf, w);
                     float mv = mix_value(S, sdf, pos, w, sv);
                     float mult = sv / mv;
                     wgt = thr * (mult * albedo) * inv_n;
+                    if (C.flags & 4u)
+                        printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) w=(%.9g %.9g %.9g) sv=%.9g mv=%.9g\n", depth, child, u01(r.x), u01(r.y), u01(r.z), w.x, w.y, w.z, sv, mv);
                     if (!isfinite(wgt)) ++n_dropped;
                     else if (wgt == 0.0f && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
                     else emit = true;

@@ -23,6 +23,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -589,6 +590,9 @@ static float ray_power(octx* c, v3 origin, v3 direction, uint32_t depth, uint32_
     if (depth < IPT_MAX_DEPTH) c->rays_at_depth[depth]++;
     osurf si = trace_geometry(c->s, origin, direction, c->use_bvh);
     olhit li = lighting_trace(c->s, origin, direction, NULL);
+    if (c->p->flags & 4u)
+        printf("CPU extend d=%u node=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) si=%d li=%d prim=%u t=%.9g\n", depth, node, origin.x, origin.y,
+               origin.z, direction.x, direction.y, direction.z, si.hit, li.hit, si.prim, si.t);
     if (li.hit) {
         if (!si.hit || vlength(vsub(si.position, origin)) > vlength(vsub(li.position, origin)))
             return isfinite(li.surface_power) ? li.surface_power : 1.0f;
@@ -603,9 +607,15 @@ static float ray_power(octx* c, v3 origin, v3 direction, uint32_t depth, uint32_
         uint32_t child = node * n_rays + i;
         draws dr = node_draws(&c->rng, child, depth + 1);
         v3 nd = mix_sample(c->s, &sdf, si.position, &dr);
-        if (vis_zero(nd)) continue; /* mix value is computed first in the reference but has no side effect */
+        if (vis_zero(nd)) {
+            if (c->p->flags & 4u) printf("CPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, dr.u[0], dr.u[1], dr.u[2]);
+            continue; /* mix value is computed first in the reference but has no side effect */
+        }
         float mix_val = mix_value(c->s, &sdf, si.position, nd);
         float sdf_val = sdf_value(&sdf, nd);
+        if (c->p->flags & 4u)
+            printf("CPU shade d=%u child=%u u=(%.9g %.9g %.9g) w=(%.9g %.9g %.9g) sv=%.9g mv=%.9g\n", depth, child, dr.u[0], dr.u[1], dr.u[2], nd.x, nd.y,
+                   nd.z, sdf_val, mix_val);
         float multiplier = sdf_val / mix_val;
         res += multiplier * mat->albedo * ray_power(c, si.position, nd, depth + 1, child);
     }

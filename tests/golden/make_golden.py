@@ -1,0 +1,115 @@
+"""Generates the golden fixtures under tests/golden/ from the UNMODIFIED reference (oracle/_ref/libipt_ref.so,
+compiled from /root/reference by `make -C oracle ref`). Run here, where /root/reference exists; the fixtures travel to
+the GPU box, the reference sources do not.
+
+    python tests/golden/make_golden.py
+
+Fixtures:
+  kat_<scene>.npz    bit-exact known answers of the reference's own functions on a fixed ray batch:
+                     Camera::sampleRay, Geometry::traceRay (hit, position, normal, curvature),
+                     Lighting::traceRayToLight (hit, position, power), camera fields, light fields.
+  ddf_kat.npz        Ddf::value known answers (src/libddf/test_ddf.cpp:181-223 and a direction sweep),
+                     AreaLight KAT (src/lighting/test_lighting.cpp:130-144), GridRenderPlane::addRay KAT.
+  image_<scene>.npz  sum / sumsq / count of the reference estimator (ray_power_recursive, n_rays=16, depth_max=4)
+                     over P passes at WxH with libc drand48, merged over forked workers seeded 1000+rank.
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+sys.path.insert(0, str(HERE.parent.parent))
+
+IMAGE_JOBS = {  # scene: (W, H, passes)
+    "box": (128, 128, 256),
+    "cornell": (128, 128, 256),
+    "corner": (64, 64, 128),
+    "openspheres": (64, 64, 128),
+}
+WORKERS = 8
+
+
+def _image_worker(args):
+    scene, W, H, passes, rank = args
+    import oracle_lib
+
+    ref = oracle_lib.load_ref()
+    h = ref.scene(scene)
+    ref.set_tree(16, 4)
+    ref.seed(1000 + rank)
+    r = ref.render(h, passes, W, H, verbatim=False)
+    return r["sum"], r["sumsq"], r["counters"], r["rays"]
+
+
+def make_images():
+    for scene, (W, H, passes) in IMAGE_JOBS.items():
+        per = passes // WORKERS
+        with mp.get_context("fork").Pool(WORKERS) as pool:
+            parts = pool.map(_image_worker, [(scene, W, H, per, k) for k in range(WORKERS)])
+        s = sum(p[0] for p in parts)
+        q = sum(p[1] for p in parts)
+        c = sum(p[2] for p in parts)
+        rays = sum(p[3] for p in parts)
+        np.savez_compressed(HERE / f"image_{scene}.npz", sum=s.astype(np.float32), sumsq=q.astype(np.float32), count=c.astype(np.uint32),
+                            passes=per * WORKERS, rays=rays, n_rays=16, depth_max=4)
+        print(scene, "mean", s.sum() / c.sum(), "rays/path", rays / (W * H * per * WORKERS))
+
+
+def make_kats():
+    import oracle_lib
+    from helpers import SCENES_ANALYTIC, ray_batch
+
+    ref = oracle_lib.load_ref()
+    for scene in SCENES_ANALYTIC + ["lightgrid:4x5"]:
+        h = ref.scene(scene)
+        o, d, xy = ray_batch(scene, lambda xy: ref.camera_rays(h, xy), n_cam_side=24, n_random=1500)
+        co, cd = ref.camera_rays(h, xy)
+        g = ref.trace_geometry(h, o, d)
+        l = ref.trace_light(h, o, d)
+        lights = np.stack([ref.light_fields(h, i) for i in range(ref.light_count(h))])
+        np.savez_compressed(HERE / f"kat_{scene.replace(':', '_')}.npz", xy=xy, cam_o=co, cam_d=cd, o=o, d=d, hit=g["hit"], pos=g["pos"],
+                            normal=g["normal"], curvature=g["curvature"], lhit=l["hit"], lpos=l["pos"], lpower=l["power"],
+                            camera=ref.camera_fields(h), lights=lights)
+        print(scene, "rays", len(o), "hits", int(g["hit"].sum()), "light hits", int(l["hit"].sum()))
+
+
+def make_ddf_kat():
+    import oracle_lib
+
+    ref = oracle_lib.load_ref()
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=(512, 3)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True).astype(np.float32)
+    fixed = np.array([[0, 0, 1], [1, 0, 0], [0, 0, -1], [0, 1, 0], [-1, 0, 0]], np.float32)  # test_ddf.cpp:185-215 directions
+    dirs = np.concatenate([fixed, v]).astype(np.float32)
+    out = {"dirs": dirs}
+    for kind, nm in [(0, "spherical"), (1, "upperhalf"), (2, "cosine"), (40, "power40")]:
+        out[nm] = ref.ddf_value(kind, dirs)
+    tos = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, -1, 0], [0.6, 0.0, 0.8], [-0.48, 0.6, -0.64]], np.float32)
+    out["tos"] = tos
+    out["cosine_rotated"] = np.stack([ref.ddf_value(2, dirs, to=t) for t in tos])
+    out["power40_rotated"] = np.stack([ref.ddf_value(40, dirs, to=t) for t in tos])
+    # AreaLight KAT (src/lighting/test_lighting.cpp:130-144)
+    area, hit, sp = ref.arealight([1, 1, 1], [-1, -1, -1], [0, -1, 0], 4.0, False, [0, 0, 0.1], [1.1, 0, 0])
+    out["arealight"] = np.array([area, float(hit), sp], np.float32)
+    area, hit, sp = ref.arealight([0, 0, 1], [1, 0, 0], [0, 1, 0], 2.0, True, [0.2, 0.2, 0], [0, 0, 1])  # back face: miss
+    out["arealight_tri_back"] = np.array([area, float(hit), sp], np.float32)
+    area, hit, sp = ref.arealight([0, 0, 1], [0, 1, 0], [1, 0, 0], 2.0, True, [0.2, 0.2, 0], [0, 0, 1])
+    out["arealight_tri_front"] = np.array([area, float(hit), sp], np.float32)
+    # GridRenderPlane::addRay KAT incl. the row mapping quirk
+    x = rng.random(4000).astype(np.float32); y = rng.random(4000).astype(np.float32); val = rng.random(4000).astype(np.float32)
+    pix, cnt, mx = ref.plane_addray(16, 12, x, y, val)
+    out.update(plane_x=x, plane_y=y, plane_v=val, plane_pixels=pix, plane_counters=cnt, plane_max=np.float32(mx))
+    np.savez_compressed(HERE / "ddf_kat.npz", **out)
+    print("ddf kat", {k: np.asarray(vv).shape for k, vv in out.items()})
+
+
+if __name__ == "__main__":
+    make_kats()
+    make_ddf_kat()
+    make_images()
