@@ -602,6 +602,11 @@ static float ray_power(octx* c, v3 origin, v3 direction, uint32_t depth, uint32_
     const ipt_material* mat = &c->s->d->materials[si.material];
     osdf sdf = make_sdf(mat, si.normal, direction);
     uint32_t n_rays = c->p->schedule[depth];
+    /* A node with n_rays == 0 (reference: n_rays/2 reaching 0, main.cpp:177) evaluates 0.0f/0 = NaN at main.cpp:181,
+     * which poisons its parent to 0 -- reachable only with non-default command-line arguments. The DRAND48 mode keeps
+     * that behaviour (it is pinned bit-exactly to the reference); the PHILOX mode, which checks the CUDA path, uses the
+     * defined extension "a split count of 0 spawns nothing and contributes 0" (include/ipt_b200.h). */
+    if (n_rays == 0 && c->rng.mode == IPT_ORACLE_RNG_PHILOX) return 0.0f;
     float res = 0.0f;
     for (uint32_t i = 0; i < n_rays; ++i) {
         uint32_t child = node * n_rays + i;

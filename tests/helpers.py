@@ -33,11 +33,12 @@ def ray_batch(scene_name, camera_rays_fn, n_cam_side=96, n_random=20000, seed=7)
     # axis-aligned and wall-grazing cases
     o2 = o[:2000].copy()
     o2[:, 2] = np.float32(-1.0)
-    d2 = unit_dirs(rng, 2000)
+    d2 = unit_dirs(rng, len(o2))
     d3 = np.zeros((600, 3), np.float32)
     for a in range(3):
         d3[a * 200:(a + 1) * 200, a] = np.where(rng.random(200) < 0.5, -1, 1)
     o3 = o[:600]
+    d3 = d3[: len(o3)]
     return np.concatenate([co, o, o2, o3]), np.concatenate([cd, d, d2, d3]), xy
 
 

@@ -100,26 +100,37 @@ def test_ddf_sampling_chi_square(kind, to, box):
     assert 0.70 < c < 1.35 and 0.95 < ratio < 1.05 and 0.95 < integral < 1.05, (c, ratio, integral)
 
 
+def histogram(dirs, n_alpha=40, n_phi=40):
+    ok = np.any(dirs != 0, axis=1)
+    d = dirs[ok]
+    alpha = np.arccos(np.clip(d[:, 2], -1, 1)); phi = np.arctan2(d[:, 1], d[:, 0]) % (2 * np.pi)
+    ia = np.minimum((alpha / np.pi * n_alpha).astype(int), n_alpha - 1); ip = np.minimum((phi / (2 * np.pi) * n_phi).astype(int), n_phi - 1)
+    h = np.zeros((n_alpha, n_phi)); np.add.at(h, (ia, ip), 1)
+    return h, ok.mean()
+
+
 @pytest.mark.parametrize("scene,xy", [("box", (0.5, 0.3)), ("box", (0.5, 0.55)), ("cornell", (0.65, 0.3)), ("corner", (0.5, 0.4)), ("lightgrid:3x3", (0.5, 0.3))])
-def test_mixture_sampling_chi_square(scene, xy, lib, oracle):
-    """The 1:1 light/sdf mixture of main.cpp:142-143 on the device: samples follow the mixture value; the values agree
-    with the oracle's UnionDdf::value / sdf value at the same directions; failed samples carry the missing mass."""
+def test_mixture_sampling_matches_oracle_distribution(scene, xy, lib, oracle):
+    """The 1:1 light/sdf mixture of main.cpp:142-143 on the device. The light is a delta-like solid angle, so instead
+    of integrating value() per bucket (check_ddf.cpp) the device histogram (40x40 buckets, as test_ddf.cpp:252-271
+    uses for `unite`) is compared with the histogram of the oracle's samples (bit-identical to the reference's, see
+    test_oracle_pin_live.py) by a two-sample chi-square; failure rates and values are compared too."""
     sd = capi.SceneDescription(scene)
     sc = capi.Scene(sd)
     o, d = oracle.camera_rays(sd.ptr, np.array([xy], np.float32))
-    w, mv, sv = sc.mix_sample(o[0], d[0], 300000, seed=777)
+    n = 300000
+    w, mv, sv = sc.mix_sample(o[0], d[0], n, seed=777)
     ok = np.any(w != 0, axis=1)
     mo, so, lo = oracle.mix_value(sd.ptr, o[0], d[0], w[ok][:5000])
     assert np.allclose(mv[ok][:5000], mo, rtol=3e-4, atol=1e-6) and np.allclose(sv[ok][:5000], so, rtol=3e-4, atol=1e-6)
-
-    def value_fn(dirs):
-        m, s, l = oracle.mix_value(sd.ptr, o[0], d[0], dirs)
-        return m
-
-    # the light is a small solid angle: finer buckets, as test_ddf.cpp:252-271 does for `unite` (40x40)
-    c, ratio, integral = chi_square(w, value_fn, 40, 40)
-    assert 0.6 < c < 1.5, c
-    assert 0.9 < ratio < 1.1, (ratio, integral)
+    oracle.seed(31337)
+    w_c, _, _ = oracle.mix_sample(sd.ptr, o[0], d[0], n)
+    hg, rate_g = histogram(w)
+    hc, rate_c = histogram(w_c)
+    assert abs(rate_g - rate_c) < 5 * np.sqrt(0.25 / n) * np.sqrt(2)
+    use = (hg + hc) > 20
+    chi2 = ((hg[use] - hc[use]) ** 2 / (hg[use] + hc[use])).sum() / use.sum()
+    assert 0.7 < chi2 < 1.35, chi2
     sc.close()
 
 
@@ -137,7 +148,14 @@ def test_converged_image_matches_reference(scene, passes, lib):
     assert np.array_equal(cnt > 0, g["count"] > 0)
     z, lit = z_scores(s.astype(np.float64), q.astype(np.float64), cnt, g["sum"].astype(np.float64), g["sumsq"].astype(np.float64), g["count"])
     assert (np.abs(z[lit]) < 3).mean() > 0.99, (np.abs(z[lit]) < 3).mean()
-    assert abs(z[lit].mean()) < 0.1, z[lit].mean()
+    # bias detector. Per-pixel z is skewed for a heavy-tailed estimator at a few hundred samples (a pixel without its
+    # rare bright path has both a low mean and a low variance estimate), so the sharp statement is on the image total:
+    # difference of the two image sums in units of its standard error.
+    assert abs(z[lit].mean()) < 0.2, z[lit].mean()
+    ng = np.maximum(cnt, 1).astype(np.float64); nc = np.maximum(g["count"], 1).astype(np.float64)
+    var_g = np.maximum(q / ng - (s / ng) ** 2, 0) / ng; var_c = np.maximum(g["sumsq"] / nc - (g["sum"] / nc) ** 2, 0) / nc
+    total_z = ((s / ng).sum() - (g["sum"] / nc).sum()) / np.sqrt(var_g.sum() + var_c.sum())
+    assert abs(total_z) < 4, total_z
     mg = s / np.maximum(cnt, 1); mc = g["sum"] / np.maximum(g["count"], 1)
     B = 8
     bg = mg[: H // B * B, : W // B * B].reshape(H // B, B, W // B, B).mean((1, 3)); bc = mc[: H // B * B, : W // B * B].reshape(H // B, B, W // B, B).mean((1, 3))
