@@ -151,6 +151,16 @@ class Oracle:
         self.lib.ipt_oracle_light_fields(desc_ptr, C.c_uint32(i), _p(out, f32p))
         return out
 
+    def bvh_build(self, triangles):
+        """The LBVH exactly as ipt_b200/csrc/ipt_lbvh.cuh builds it: (nodes, sorted ids, sorted Morton keys)."""
+        from ipt_b200.capi import BVH_NODE_DTYPE
+
+        t = _f32(triangles).reshape(-1, 9)
+        n = t.shape[0]
+        nodes = np.zeros(max(n - 1, 0), BVH_NODE_DTYPE); ids = np.empty(n, np.uint32); keys = np.empty(n, np.uint64)
+        self.lib.ipt_oracle_bvh_build(_p(t, f32p), C.c_uint64(n), nodes.ctypes.data_as(C.c_void_p), _p(ids, u32p), _p(keys, u64p))
+        return nodes, ids, keys
+
     def philox(self, c, k):
         out = (C.c_uint32 * 4)()
         self.lib.ipt_oracle_philox(*[C.c_uint32(v) for v in c], *[C.c_uint32(v) for v in k], out)
