@@ -174,6 +174,9 @@ int ipt_scene_set_camera(ipt_scene* scene, const ipt_camera* camera);
  * The returned description and its arrays are owned by the library until ipt_scene_desc_free. */
 int ipt_sample_scene(const char* name, ipt_scene_desc** out);
 int ipt_scene_desc_free(ipt_scene_desc* desc);
+/* What the Light constructors derive (AreaLight::AreaLight lighting.cpp:79-90, SphereLight lighting.h:46-53):
+ * Light::area, power/area, and for area lights normalize(cross(x,y)). Host arithmetic in glm operation order. */
+int ipt_light_derived(const ipt_light* light, float* area, float* surface_power, float normal[3]);
 /* SimpleCamera::SimpleCamera (src/SimpleCamera.cpp:8-13) */
 int ipt_camera_look(const float position[3], const float direction[3], const float up_hint[3], ipt_camera* out);
 
@@ -197,6 +200,8 @@ int ipt_mix_sample(ipt_scene* scene, const float origin[3], const float directio
                    float* dirs, float* mix_value, float* sdf_value);
 /* Lighting::distributionInPoint(pos)->value(dir) (CollectionLighting.cpp:12-21, lighting.cpp:61-73). */
 int ipt_light_ddf_value(ipt_scene* scene, const float pos[3], const float* dirs, size_t n, float* out);
+/* Lighting::distributionInPoint(pos)->sample(): n directions (zero vector = failed sample), Philox stream (seed, index). */
+int ipt_light_ddf_sample(ipt_scene* scene, const float pos[3], uint64_t seed, size_t n, float* dirs);
 
 /* LBVH over the triangle mesh, as built on the device: n_triangles-1 internal nodes of 64 bytes (root = 0), each
  * holding BOTH children's boxes; the sorted primitive order; the sorted 63-bit Morton keys. */
@@ -218,6 +223,8 @@ int ipt_plane_create(ipt_scene* scene, uint32_t width, uint32_t height, ipt_plan
 int ipt_plane_wrap(ipt_scene* scene, uint32_t width, uint32_t height, float* d_sum, float* d_sumsq, uint32_t* d_count,
                    ipt_plane** out);
 int ipt_plane_clear(ipt_plane* plane);
+/* RenderPlane::addRay itself (tracer_interfaces.h:53) for n samples given in HOST memory: cell mapping per plane_mode. */
+int ipt_plane_add_rays(ipt_plane* plane, uint32_t plane_mode, size_t n, const float* x, const float* y, const float* value);
 int ipt_plane_destroy(ipt_plane* plane);
 int ipt_plane_download(ipt_plane* plane, float* sum, float* sumsq, uint32_t* count);     /* device -> host */
 int ipt_plane_upload(ipt_plane* plane, const float* sum, const float* sumsq, const uint32_t* count); /* resume */

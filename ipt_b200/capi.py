@@ -91,6 +91,7 @@ SIGNATURES = {
     "ipt_scene_set_camera": (C.c_int, [_vp, C.POINTER(Camera)]),
     "ipt_sample_scene": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(SceneDesc))]),
     "ipt_scene_desc_free": (C.c_int, [C.POINTER(SceneDesc)]),
+    "ipt_light_derived": (C.c_int, [C.POINTER(Light), f32p, f32p, f32p]),
     "ipt_camera_look": (C.c_int, [f32p, f32p, f32p, C.POINTER(Camera)]),
     "ipt_trace_batch": (C.c_int, [_vp, f32p, f32p, C.c_size_t, u32p, f32p, u32p, f32p, u32p]),
     "ipt_camera_rays": (C.c_int, [_vp, f32p, C.c_size_t, f32p, f32p]),
@@ -98,10 +99,12 @@ SIGNATURES = {
     "ipt_ddf_sample": (C.c_int, [_vp, C.c_int, f32p, C.c_uint64, C.c_size_t, f32p]),
     "ipt_mix_sample": (C.c_int, [_vp, f32p, f32p, C.c_uint64, C.c_size_t, f32p, f32p, f32p]),
     "ipt_light_ddf_value": (C.c_int, [_vp, f32p, f32p, C.c_size_t, f32p]),
+    "ipt_light_ddf_sample": (C.c_int, [_vp, f32p, C.c_uint64, C.c_size_t, f32p]),
     "ipt_bvh_export": (C.c_int, [_vp, C.POINTER(BvhNode), u32p, u64p, u64p]),
     "ipt_plane_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
     "ipt_plane_wrap": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
     "ipt_plane_clear": (C.c_int, [_vp]),
+    "ipt_plane_add_rays": (C.c_int, [_vp, C.c_uint32, C.c_size_t, f32p, f32p, f32p]),
     "ipt_plane_destroy": (C.c_int, [_vp]),
     "ipt_plane_download": (C.c_int, [_vp, f32p, f32p, u32p]),
     "ipt_plane_upload": (C.c_int, [_vp, f32p, f32p, u32p]),
@@ -252,6 +255,12 @@ class Scene:
         check(load().ipt_light_ddf_value(self.handle, _ptr(p, f32p), _ptr(w, f32p), w.shape[0], _ptr(out, f32p)))
         return out
 
+    def light_ddf_sample(self, pos, n, seed=0):
+        p = _f32(pos)
+        w = np.empty((n, 3), np.float32)
+        check(load().ipt_light_ddf_sample(self.handle, _ptr(p, f32p), seed, n, _ptr(w, f32p)))
+        return w
+
     def bvh_export(self):
         n_nodes = C.c_uint64(0)
         check(load().ipt_bvh_export(self.handle, None, None, None, C.byref(n_nodes)))
@@ -290,6 +299,10 @@ class Plane:
         st = RenderStats()
         check(load().ipt_render(self.scene.handle, self.handle, C.byref(params), C.byref(st)))
         return st
+
+    def add_rays(self, x, y, v, mode=PLANE_GRID):
+        x, y, v = _f32(x), _f32(y), _f32(v)
+        check(load().ipt_plane_add_rays(self.handle, mode, len(x), _ptr(x, f32p), _ptr(y, f32p), _ptr(v, f32p)))
 
     def download(self):
         n = self.width * self.height

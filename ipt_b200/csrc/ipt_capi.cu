@@ -159,6 +159,28 @@ __global__ void k_light_ddf_value(const __grid_constant__ DevScene S, f3 pos, co
     out[i] = S.n_lights ? v / (1.0f - S.sdf_weight) : 0.0f;
 }
 
+__global__ void k_light_ddf_sample(const __grid_constant__ DevScene S, f3 pos, uint32_t k0, uint32_t k1, size_t n, float* w) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 2u, 0xDDF2u, k0, k1);
+    // UnionDdf::sample over the lights alone: the draw is scaled into the light half of the 1:1 mixture's cdf
+    float us = u01(r.x) * (1.0f - S.sdf_weight);
+    Sdf dummy{};
+    Basis bn{};
+    f3 x = S.n_lights ? mix_sample(S, dummy, bn, pos, us, u01(r.y), u01(r.z), u01(r.w)) : mk3(0, 0, 0);
+    if (S.n_lights && !(us < (S.light_inline ? S.lights[S.n_lights - 1].cdf : S.lights_g[S.n_lights - 1].cdf))) x = mk3(0, 0, 0);
+    w[3 * i] = x.x; w[3 * i + 1] = x.y; w[3 * i + 2] = x.z;
+}
+
+__global__ void k_plane_add_rays(RenderCtx C, size_t n, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t cell = plane_cell(C, x[i], y[i], min((uint32_t)(x[i] * C.width), C.width - 1), min((uint32_t)(y[i] * C.height), C.height - 1));
+    atomicAdd(&C.sum[cell], v[i]);
+    atomicAdd(&C.sumsq[cell], v[i] * v[i]);
+    atomicAdd(&C.count[cell], 1u);
+}
+
 __global__ void k_plane_resolve(const float* __restrict__ sum, const uint32_t* __restrict__ count, size_t n, float* pixels) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pixels[i] = count[i] ? sum[i] / (float)count[i] : 0.0f;
@@ -297,6 +319,21 @@ int ipt_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int ipt_light_derived(const ipt_light* light, float* area, float* surface_power, float normal[3]) {
+    if (!light) return fail(IPT_ERR_INVALID, "null light");
+    ipt_scene_desc d{};
+    d.n_lights = 1;
+    d.lights = light;
+    std::vector<DevLight> out;
+    float w;
+    int rc = flatten_lights(&d, out, w);
+    if (rc) return rc;
+    if (area) *area = out[0].area;
+    if (surface_power) *surface_power = out[0].surface_power;
+    if (normal) { normal[0] = out[0].nx; normal[1] = out[0].ny; normal[2] = out[0].nz; }
+    return IPT_OK;
 }
 
 int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
@@ -533,6 +570,19 @@ int ipt_light_ddf_value(ipt_scene* s, const float pos[3], const float* dirs, siz
     return IPT_OK;
 }
 
+int ipt_light_ddf_sample(ipt_scene* s, const float pos[3], uint64_t seed, size_t n, float* dirs) {
+    if (!s || !pos || !dirs) return fail(IPT_ERR_INVALID, "null argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_w;
+    CUDA_TRY(d_w.alloc(3 * n));
+    k_light_ddf_sample<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->dev, f3{pos[0], pos[1], pos[2]}, (uint32_t)seed, (uint32_t)(seed >> 32), n, d_w.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dirs, d_w.p, 12 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return IPT_OK;
+}
+
 int ipt_bvh_export(ipt_scene* s, ipt_bvh_node* nodes, uint32_t* sorted_prims, uint64_t* morton, uint64_t* n_nodes) {
     if (!s) return fail(IPT_ERR_INVALID, "null scene");
     if (!s->mesh) return fail(IPT_ERR_INVALID, "scene has no triangle mesh");
@@ -576,6 +626,25 @@ int ipt_plane_clear(ipt_plane* p) {
     CUDA_TRY(cudaMemsetAsync(p->sumsq, 0, 4 * n, p->scene->stream));
     CUDA_TRY(cudaMemsetAsync(p->count, 0, 4 * n, p->scene->stream));
     CUDA_TRY(cudaStreamSynchronize(p->scene->stream));
+    return IPT_OK;
+}
+int ipt_plane_add_rays(ipt_plane* p, uint32_t plane_mode, size_t n, const float* x, const float* y, const float* value) {
+    if (!p || !x || !y || !value || plane_mode > IPT_PLANE_LINEAR) return fail(IPT_ERR_INVALID, "bad argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(p->scene->device));
+    cudaStream_t st = p->scene->stream;
+    DevBuf<float> d_x, d_y, d_v;
+    CUDA_TRY(d_x.alloc(n)); CUDA_TRY(d_y.alloc(n)); CUDA_TRY(d_v.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(d_x.p, x, 4 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_y.p, y, 4 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_v.p, value, 4 * n, cudaMemcpyHostToDevice, st));
+    RenderCtx C;
+    std::memset(&C, 0, sizeof C);
+    C.sum = p->sum; C.sumsq = p->sumsq; C.count = p->count;
+    C.width = p->width; C.height = p->height; C.plane_mode = plane_mode;
+    k_plane_add_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(C, n, d_x.p, d_y.p, d_v.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
     return IPT_OK;
 }
 int ipt_plane_destroy(ipt_plane* p) {

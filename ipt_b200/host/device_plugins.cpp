@@ -1,0 +1,430 @@
+// device_plugins.cpp — see device_plugins.hpp. Marshals the reference-facing C++ objects to the C ABI.
+#include "device_plugins.hpp"
+
+#include "glm_order.hpp"
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+namespace ipt_b200 {
+
+namespace H = ipt_host;
+
+void check(int status) {
+    if (status != IPT_OK) throw Error(status, std::string("ipt_b200: ") + ipt_last_error());
+}
+
+static H::f3 h3(glm::vec3 v) { return H::mk(v.x, v.y, v.z); }
+static glm::vec3 g3(H::f3 v) { return glm::vec3(v.x, v.y, v.z); }
+static void put(float* p, glm::vec3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+static ipt_material lambert() { return ipt_material{IPT_DDF_COSINE, 1.0f, 1.0f, 0.0f, 0.0f}; }
+static std::atomic<uint64_t> g_sample_counter{1};
+
+ipt_scene_desc SceneBuilder::desc() const {
+    ipt_scene_desc d{};
+    d.n_prims = (uint32_t)prims.size();
+    d.prims = prims.data();
+    d.n_materials = (uint32_t)materials.size();
+    d.materials = materials.data();
+    d.n_lights = (uint32_t)lights.size();
+    d.lights = lights.data();
+    d.n_triangles = triangles.size() / 9;
+    d.triangles = triangles.empty() ? nullptr : triangles.data();
+    d.triangle_material = triangle_material;
+    d.camera = camera;
+    return d;
+}
+
+DeviceContext::DeviceContext(const SceneBuilder& b, int device) : desc_(b) {
+    if (desc_.materials.empty()) desc_.materials.push_back(lambert());
+    if (!desc_.has_camera) { // a camera is not needed for single-ray queries; give the description a valid one
+        const float p[3] = {0, -3, 0}, d[3] = {0, 1, 0}, u[3] = {0, 0, 1};
+        check(ipt_camera_look(p, d, u, &desc_.camera));
+    }
+    ipt_scene_desc d = desc_.desc();
+    check(ipt_scene_create(&d, device, &scene_));
+}
+DeviceContext::~DeviceContext() {
+    if (scene_) ipt_scene_destroy(scene_);
+}
+
+// ---- DDFs handed out through the interfaces: evaluated on the device ------------------------------------
+class DeviceSdf : public Ddf {
+public:
+    DeviceSdf(std::shared_ptr<DeviceContext> ctx, ipt_material m, glm::vec3 n, glm::vec3 refl) : ctx_(std::move(ctx)), m_(m), n_(n), refl_(refl) {}
+    glm::vec3 sample() const override {
+        if (m_.ddf == IPT_DDF_COSINE) return one(2, n_);
+        // kd*Lambert + ks*PowerCosine about the mirror direction; below-surface directions are failed samples
+        float wd = m_.kd / (m_.kd + m_.ks);
+        uint64_t c = g_sample_counter.fetch_add(1);
+        float u = (float)((c * 0x9E3779B97F4A7C15ull) >> 40) * (1.0f / 16777216.0f);
+        glm::vec3 w = u < wd ? one(2, n_) : one((int)m_.exponent, refl_);
+        if (H::dot(h3(n_), h3(w)) < 0.0f) return glm::vec3();
+        return w;
+    }
+    float value(glm::vec3 w) const override {
+        if (m_.ddf == IPT_DDF_COSINE) return val(2, n_, w);
+        if (H::dot(h3(n_), h3(w)) < 0.0f) return 0.0f;
+        float wd = m_.kd / (m_.kd + m_.ks), ws = m_.ks / (m_.kd + m_.ks);
+        return wd * val(2, n_, w) + ws * val((int)m_.exponent, refl_, w);
+    }
+
+private:
+    glm::vec3 one(int kind, glm::vec3 to) const {
+        float t[3], out[3];
+        put(t, to);
+        check(ipt_ddf_sample(ctx_->scene(), kind, t, g_sample_counter.fetch_add(1), 1, out));
+        return glm::vec3(out[0], out[1], out[2]);
+    }
+    float val(int kind, glm::vec3 to, glm::vec3 w) const {
+        float t[3], d[3], out;
+        put(t, to);
+        put(d, w);
+        check(ipt_ddf_value(ctx_->scene(), kind, t, d, 1, &out));
+        return out;
+    }
+    std::shared_ptr<DeviceContext> ctx_;
+    ipt_material m_;
+    glm::vec3 n_, refl_;
+};
+
+class DeviceLightDdf : public Ddf {
+public:
+    DeviceLightDdf(std::shared_ptr<DeviceContext> ctx, glm::vec3 pos) : ctx_(std::move(ctx)), pos_(pos) {}
+    glm::vec3 sample() const override {
+        float p[3], out[3];
+        put(p, pos_);
+        check(ipt_light_ddf_sample(ctx_->scene(), p, g_sample_counter.fetch_add(1), 1, out));
+        return glm::vec3(out[0], out[1], out[2]);
+    }
+    float value(glm::vec3 w) const override {
+        float p[3], d[3], out;
+        put(p, pos_);
+        put(d, w);
+        check(ipt_light_ddf_value(ctx_->scene(), p, d, 1, &out));
+        return out;
+    }
+
+private:
+    std::shared_ptr<DeviceContext> ctx_;
+    glm::vec3 pos_;
+};
+
+// ---- DeviceGeometry -------------------------------------------------------------------------------------
+uint32_t DeviceGeometry::addMaterial(const ipt_material& m) {
+    data_.materials.push_back(m);
+    ctx_.reset();
+    return (uint32_t)data_.materials.size() - 1;
+}
+void DeviceGeometry::addBoxPlane(glm::vec3 plane, uint32_t material) {
+    ipt_prim p{};
+    p.kind = IPT_PRIM_BOX_PLANE;
+    p.material = material;
+    put(p.p, plane);
+    data_.prims.push_back(p);
+    ctx_.reset();
+}
+void DeviceGeometry::addSphere(glm::vec3 centre, float radius, float curvature, uint32_t material) {
+    ipt_prim p{};
+    p.kind = IPT_PRIM_SPHERE;
+    p.material = material;
+    put(p.p, centre);
+    p.radius = radius;
+    p.curvature = curvature;
+    data_.prims.push_back(p);
+    ctx_.reset();
+}
+void DeviceGeometry::addSmallPtSphere(glm::vec3 centre, float radius, uint32_t material) {
+    ipt_prim p{};
+    p.kind = IPT_PRIM_SPHERE_SMALLPT;
+    p.material = material;
+    put(p.p, centre);
+    p.radius = radius;
+    p.flip_normal = radius < 100 ? 0 : 1; // GeometrySmallPt.cpp:53
+    p.curvature = (float)(-1.0 / (double)radius);
+    data_.prims.push_back(p);
+    ctx_.reset();
+}
+void DeviceGeometry::setTriangles(const float* t, size_t count, uint32_t material) {
+    data_.triangles.assign(t, t + 9 * count);
+    data_.triangle_material = material;
+    ctx_.reset();
+}
+std::shared_ptr<DeviceGeometry> DeviceGeometry::fromSampleScene(const char* name) {
+    ipt_scene_desc* d = nullptr;
+    check(ipt_sample_scene(name, &d));
+    auto g = std::make_shared<DeviceGeometry>();
+    g->data_.prims.assign(d->prims, d->prims + d->n_prims);
+    g->data_.materials.assign(d->materials, d->materials + d->n_materials);
+    if (d->n_triangles) g->data_.triangles.assign(d->triangles, d->triangles + 9 * d->n_triangles);
+    g->data_.triangle_material = d->triangle_material;
+    ipt_scene_desc_free(d);
+    return g;
+}
+void DeviceGeometry::exportTo(SceneBuilder& b) const {
+    b.prims = data_.prims;
+    b.materials = data_.materials.empty() ? std::vector<ipt_material>{lambert()} : data_.materials;
+    b.triangles = data_.triangles;
+    b.triangle_material = data_.triangle_material;
+}
+DeviceContext& DeviceGeometry::context() const {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (!ctx_) {
+        SceneBuilder b;
+        exportTo(b);
+        ctx_ = std::make_shared<DeviceContext>(b);
+    }
+    return *ctx_;
+}
+std::optional<surface_intersection> DeviceGeometry::traceRay(glm::vec3 origin, glm::vec3 direction) const {
+    DeviceContext& c = context();
+    float o[3], d[3], t;
+    uint32_t prim;
+    put(o, origin);
+    put(d, direction);
+    check(ipt_trace_batch(c.scene(), o, d, 1, &prim, &t, nullptr, nullptr, nullptr));
+    if (prim == IPT_NO_HIT) return {};
+    const SceneBuilder& sb = c.description();
+    surface_intersection res;
+    res.position = g3(h3(origin) + h3(direction) * t); // origin + direction*dist (GeometrySphereInBox.cpp:42)
+    uint32_t material;
+    if (prim >= sb.prims.size()) {
+        const float* tri = sb.triangles.data() + 9 * (size_t)(prim - sb.prims.size());
+        res.normal = g3(H::normalize(H::cross(H::mk(tri + 3), H::mk(tri + 6))));
+        res.curvature = 0.0f;
+        material = sb.triangle_material;
+    } else {
+        const ipt_prim& p = sb.prims[prim];
+        material = p.material;
+        res.curvature = p.curvature;
+        if (p.kind == IPT_PRIM_BOX_PLANE) res.normal = glm::vec3(-p.p[0], -p.p[1], -p.p[2]);
+        else {
+            H::f3 n = H::normalize(h3(res.position) - H::mk(p.p));
+            res.normal = g3(p.flip_normal ? -n : n);
+        }
+    }
+    const ipt_material& m = sb.materials[material];
+    H::f3 I = h3(direction), N = h3(res.normal);
+    glm::vec3 refl = g3(I - N * H::dot(N, I) * 2.0f); // glm::reflect
+    res.sdf = std::make_unique<DeviceSdf>(ctx_, m, res.normal, refl);
+    res.albedo = m.albedo;
+    return res;
+}
+
+// ---- DeviceLighting -------------------------------------------------------------------------------------
+void DeviceLighting::addPointLight(glm::vec3 position, float, float power) {
+    ipt_light l{};
+    l.kind = IPT_LIGHT_POINT;
+    put(l.position, position);
+    l.power = power;
+    addLight(l);
+}
+void DeviceLighting::addSphereLight(glm::vec3 position, float radius, float power) {
+    ipt_light l{};
+    l.kind = IPT_LIGHT_SPHERE;
+    put(l.position, position);
+    l.radius = radius;
+    l.power = power;
+    addLight(l);
+}
+void DeviceLighting::addSquareLight(glm::vec3 corner, glm::vec3 normal, glm::vec3 x_side, float power) {
+    ipt_light l{};
+    l.kind = IPT_LIGHT_AREA_DIAMOND;
+    put(l.position, corner);
+    put(l.x_axis, x_side);
+    put(l.y_axis, g3(H::cross(h3(normal), h3(x_side)))); // CollectionLighting.cpp:43
+    l.power = power;
+    addLight(l);
+}
+void DeviceLighting::addTriangleLight(glm::vec3 corner, glm::vec3 x_side, glm::vec3 y_side, float power) {
+    ipt_light l{};
+    l.kind = IPT_LIGHT_AREA_TRIANGLE;
+    put(l.position, corner);
+    put(l.x_axis, x_side);
+    put(l.y_axis, y_side);
+    l.power = power;
+    addLight(l);
+}
+void DeviceLighting::addOuterLight(float radius, float power) {
+    ipt_light l{};
+    l.kind = IPT_LIGHT_SPHERE_INVERTED; // CollectionLighting.cpp:52-55
+    l.radius = radius;
+    l.power = power;
+    addLight(l);
+}
+void DeviceLighting::exportTo(SceneBuilder& b) const { b.lights = lights_; }
+DeviceContext& DeviceLighting::context() const {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (!ctx_) {
+        SceneBuilder b;
+        exportTo(b);
+        ctx_ = std::make_shared<DeviceContext>(b);
+    }
+    return *ctx_;
+}
+std::unique_ptr<Ddf> DeviceLighting::distributionInPoint(glm::vec3 pos) const {
+    context();
+    return std::make_unique<DeviceLightDdf>(ctx_, pos);
+}
+std::optional<light_intersection> DeviceLighting::traceRayToLight(glm::vec3 origin, glm::vec3 direction) const {
+    DeviceContext& c = context();
+    float o[3], d[3], lp[3];
+    uint32_t light;
+    put(o, origin);
+    put(d, direction);
+    check(ipt_trace_batch(c.scene(), o, d, 1, nullptr, nullptr, &light, lp, nullptr));
+    if (light == IPT_NO_HIT) return {};
+    const ipt_light& l = lights_[light];
+    light_intersection res;
+    res.position = glm::vec3(lp[0], lp[1], lp[2]);
+    float area, sp, n[3];
+    check(ipt_light_derived(&l, &area, &sp, n));
+    res.surface_power = sp;
+    if (l.kind <= IPT_LIGHT_AREA_TRIANGLE) res.normal = glm::vec3(n[0], n[1], n[2]);
+    else {
+        H::f3 nn = H::normalize(h3(res.position) - H::mk(l.position));
+        res.normal = g3(l.kind == IPT_LIGHT_SPHERE_INVERTED ? -nn : nn);
+    }
+    return res;
+}
+
+// ---- DeviceCamera -----------------------------------------------------------------------------------------
+DeviceCamera::DeviceCamera(glm::vec3 p, glm::vec3 d, glm::vec3 up_hint) : position(p), direction(d) {
+    float pp[3], dd[3], uu[3];
+    put(pp, p);
+    put(dd, d);
+    put(uu, up_hint);
+    ipt_camera c;
+    check(ipt_camera_look(pp, dd, uu, &c));
+    right = glm::vec3(c.right[0], c.right[1], c.right[2]);
+    up = glm::vec3(c.up[0], c.up[1], c.up[2]);
+}
+void DeviceCamera::exportTo(SceneBuilder& b) const {
+    put(b.camera.position, position);
+    put(b.camera.direction, direction);
+    put(b.camera.right, right);
+    put(b.camera.up, up);
+    b.has_camera = true;
+}
+std::pair<glm::vec3, glm::vec3> DeviceCamera::sampleRay(float x, float y) const {
+    SceneBuilder b;
+    exportTo(b);
+    if (!ctx_) ctx_ = std::make_shared<DeviceContext>(b);
+    check(ipt_scene_set_camera(ctx_->scene(), &b.camera)); // the fields are public and may have been changed
+    float xy[2] = {x, y}, o[3], d[3];
+    check(ipt_camera_rays(ctx_->scene(), xy, 1, o, d));
+    return {glm::vec3(o[0], o[1], o[2]), glm::vec3(d[0], d[1], d[2])};
+}
+
+// ---- DevicePlane --------------------------------------------------------------------------------------------
+DevicePlane::DevicePlane(size_t w, size_t h) : width(w), height(h) {
+    pixels.resize(w * h);
+    pixel_counters.resize(w * h);
+}
+DevicePlane::~DevicePlane() {
+    if (plane_) ipt_plane_destroy(plane_);
+}
+ipt_plane* DevicePlane::attach(const std::shared_ptr<DeviceContext>& ctx) {
+    if (plane_ && ctx_ == ctx) return plane_;
+    std::vector<float> s, q;
+    std::vector<uint32_t> c;
+    bool carry = plane_ != nullptr;
+    if (carry) {
+        sums(s, q, c);
+        ipt_plane_destroy(plane_);
+        plane_ = nullptr;
+    }
+    ctx_ = ctx;
+    check(ipt_plane_create(ctx_->scene(), (uint32_t)width, (uint32_t)height, &plane_));
+    if (carry) check(ipt_plane_upload(plane_, s.data(), q.data(), c.data()));
+    return plane_;
+}
+void DevicePlane::addRay(float x, float y, float value) {
+    if (!plane_) attach(std::make_shared<DeviceContext>(SceneBuilder()));
+    check(ipt_plane_add_rays(plane_, plane_mode, 1, &x, &y, &value));
+}
+void DevicePlane::sums(std::vector<float>& sum, std::vector<float>& sumsq, std::vector<uint32_t>& count) {
+    sum.assign(width * height, 0.0f);
+    sumsq.assign(width * height, 0.0f);
+    count.assign(width * height, 0u);
+    if (plane_) check(ipt_plane_download(plane_, sum.data(), sumsq.data(), count.data()));
+}
+void DevicePlane::download() {
+    if (!plane_) return;
+    std::vector<uint64_t> cnt(width * height);
+    check(ipt_plane_resolve(plane_, pixels.data(), cnt.data(), &max_value));
+    for (size_t i = 0; i < cnt.size(); ++i) pixel_counters[i] = (size_t)cnt[i];
+}
+
+// ---- factory ------------------------------------------------------------------------------------------------
+Scene make_scene(const char* name) {
+    ipt_scene_desc* d = nullptr;
+    check(ipt_sample_scene(name, &d));
+    auto lighting = std::make_shared<DeviceLighting>();
+    for (uint32_t i = 0; i < d->n_lights; ++i) lighting->addLight(d->lights[i]);
+    auto camera = std::make_shared<DeviceCamera>(glm::vec3(0, 0, 0), glm::vec3(0, 1, 0));
+    camera->position = glm::vec3(d->camera.position[0], d->camera.position[1], d->camera.position[2]);
+    camera->direction = glm::vec3(d->camera.direction[0], d->camera.direction[1], d->camera.direction[2]);
+    camera->right = glm::vec3(d->camera.right[0], d->camera.right[1], d->camera.right[2]);
+    camera->up = glm::vec3(d->camera.up[0], d->camera.up[1], d->camera.up[2]);
+    ipt_scene_desc_free(d);
+    return Scene{DeviceGeometry::fromSampleScene(name), lighting, camera};
+}
+
+// ---- the hot path ---------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_cache_mu;
+std::map<std::tuple<const void*, const void*, const void*, int>, std::shared_ptr<DeviceContext>> g_cache;
+}
+
+ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, int device) {
+    const DeviceExportable* g = dynamic_cast<const DeviceExportable*>(scene.geometry.get());
+    const DeviceExportable* l = dynamic_cast<const DeviceExportable*>(scene.lighting.get());
+    const DeviceExportable* c = dynamic_cast<const DeviceExportable*>(scene.camera.get());
+    if (!g || !l || !c)
+        throw Error(IPT_ERR_UNSUPPORTED,
+                    "ipt_b200::render_sample: every Scene member must be DeviceExportable (DeviceGeometry / DeviceLighting / "
+                    "DeviceCamera); the reference's own classes hide their data and there is no CPU fallback");
+    std::shared_ptr<DeviceContext> ctx;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        auto key = std::make_tuple((const void*)scene.geometry.get(), (const void*)scene.lighting.get(), (const void*)scene.camera.get(), device);
+        auto it = g_cache.find(key);
+        if (it == g_cache.end()) {
+            SceneBuilder b;
+            g->exportTo(b);
+            l->exportTo(b);
+            c->exportTo(b);
+            it = g_cache.emplace(key, std::make_shared<DeviceContext>(b, device)).first;
+        }
+        ctx = it->second;
+    }
+    SceneBuilder cam;
+    c->exportTo(cam); // the camera may be orbited between calls (gui.cpp:107-137): always refresh it
+    check(ipt_scene_set_camera(ctx->scene(), &cam.camera));
+    ipt_render_stats stats{};
+    if (DevicePlane* dp = dynamic_cast<DevicePlane*>(&r_plane)) {
+        ipt_render_params p = params;
+        p.plane_mode = dp->plane_mode;
+        check(ipt_render(ctx->scene(), dp->attach(ctx), &p, &stats));
+        return stats;
+    }
+    // foreign RenderPlane: accumulate per loop pixel, then one addRay per pixel with the mean at the pixel centre
+    ipt_render_params p = params;
+    p.plane_mode = IPT_PLANE_LINEAR;
+    size_t n = (size_t)p.width * p.height;
+    std::vector<float> sum(n), sumsq(n);
+    std::vector<uint32_t> count(n);
+    check(ipt_render_host(ctx->scene(), &p, sum.data(), sumsq.data(), count.data(), &stats));
+    for (uint32_t iy = 0; iy < p.height; ++iy)
+        for (uint32_t ix = 0; ix < p.width; ++ix) {
+            size_t i = (size_t)iy * p.width + ix;
+            if (count[i]) r_plane.addRay((ix + 0.5f) / p.width, (iy + 0.5f) / p.height, sum[i] / count[i]);
+        }
+    return stats;
+}
+
+} // namespace ipt_b200

@@ -1,0 +1,163 @@
+// device_plugins.hpp — C++ host classes that put the CUDA trace loop behind the reference's own abstractions
+// (src/tracer_interfaces.h:26-54): Geometry, Lighting, Camera, RenderPlane, Scene.
+//
+// The reference's loop is   render_sample(const Scene&, RenderPlane&, StatsNode*)   (src/main.cpp:186-223), called in
+// a loop from main.cpp:264. The drop-in is
+//
+//     ipt_b200::render_sample(scene, plane, params);          // params.pass_count calls of render_sample at once
+//
+// with `scene` built from the classes below, which mirror the reference's factory API one to one
+// (CollectionLighting::add*Light, SimpleCamera, the Geometry* classes) but, unlike the reference's classes
+// (SURVEY.md S12), can describe themselves to the device (`DeviceExportable`).
+//
+// Every virtual of the reference interfaces is implemented by CALLING THE DEVICE through the C ABI for that one
+// ray / point (there is no CPU implementation of the arithmetic anywhere in this library); they exist so that the
+// objects remain usable by code written against tracer_interfaces.h (e.g. ray_power_preview, main.cpp:55-92), not
+// for throughput. Include path decides which interface header is used: the reference's own
+// (-I<reference>/src -I<reference>/include first) or the mirror in host/compat/.
+#pragma once
+#include "tracer_interfaces.h"
+
+#include "ipt_b200.h"
+
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ipt_b200 {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+void check(int status); // throws Error with ipt_last_error()
+
+// What a scene member contributes to the flat description the device consumes.
+struct SceneBuilder {
+    std::vector<ipt_prim> prims;
+    std::vector<ipt_material> materials;
+    std::vector<ipt_light> lights;
+    std::vector<float> triangles;
+    uint32_t triangle_material = 0;
+    ipt_camera camera{};
+    bool has_camera = false;
+    ipt_scene_desc desc() const;
+};
+struct DeviceExportable {
+    virtual void exportTo(SceneBuilder& b) const = 0;
+    virtual ~DeviceExportable() {}
+};
+
+// Shared device state of one Scene (scene handle + lazily created planes), created on first use.
+class DeviceContext {
+public:
+    explicit DeviceContext(const SceneBuilder& b, int device = 0);
+    ~DeviceContext();
+    ipt_scene* scene() const { return scene_; }
+    const SceneBuilder& description() const { return desc_; }
+
+private:
+    SceneBuilder desc_;
+    ipt_scene* scene_ = nullptr;
+};
+
+// ---- Geometry ---------------------------------------------------------------------------------------
+// One class for every reference geometry (GeometrySphereInBox, GeometryFloor, GeometryCorner, GeometryOpenSpheres,
+// FractalSpheres, GeometrySmallPt) and the mesh extension: an ordered primitive list.
+class DeviceGeometry : public Geometry, public DeviceExportable {
+public:
+    uint32_t addMaterial(const ipt_material& m);
+    void addBoxPlane(glm::vec3 plane, uint32_t material = 0);                              // geometric_utils.cpp:8
+    void addSphere(glm::vec3 centre, float radius, float curvature, uint32_t material = 0); // geometric_utils.cpp:28
+    void addSmallPtSphere(glm::vec3 centre, float radius, uint32_t material = 0);          // GeometrySmallPt.cpp:13-23
+    void setTriangles(const float* v0_e1_e2, size_t count, uint32_t material = 0);
+    static std::shared_ptr<DeviceGeometry> fromSampleScene(const char* name);              // "box", "cornell", ...
+
+    std::optional<surface_intersection> traceRay(glm::vec3 origin, glm::vec3 direction) const override;
+    void exportTo(SceneBuilder& b) const override;
+
+private:
+    friend class DeviceSdf;
+    SceneBuilder data_;
+    mutable std::shared_ptr<DeviceContext> ctx_; // geometry-only context used by traceRay()
+    mutable std::mutex mu_;
+    DeviceContext& context() const;
+};
+
+// ---- Lighting: CollectionLighting's API (src/CollectionLighting.h:10-21) ------------------------------
+class DeviceLighting : public Lighting, public DeviceExportable {
+public:
+    void addPointLight(glm::vec3 position, float virtual_radius, float power = 1.0f);
+    void addSphereLight(glm::vec3 position, float radius, float power = 1.0f);
+    void addSquareLight(glm::vec3 corner, glm::vec3 normal, glm::vec3 x_side, float power = 1.0f);
+    void addTriangleLight(glm::vec3 corner, glm::vec3 x_side, glm::vec3 y_side, float power = 1.0f);
+    void addOuterLight(float radius, float power = 1.0f);
+    void addLight(const ipt_light& l) { lights_.push_back(l); ctx_.reset(); }
+    size_t size() const { return lights_.size(); }
+
+    std::unique_ptr<Ddf> distributionInPoint(glm::vec3 pos) const override;
+    std::optional<light_intersection> traceRayToLight(glm::vec3 origin, glm::vec3 direction) const override;
+    void exportTo(SceneBuilder& b) const override;
+
+private:
+    friend class DeviceLightDdf;
+    std::vector<ipt_light> lights_;
+    mutable std::shared_ptr<DeviceContext> ctx_;
+    mutable std::mutex mu_;
+    DeviceContext& context() const;
+};
+
+// ---- Camera: SimpleCamera (src/SimpleCamera.h:10-17) ---------------------------------------------------
+class DeviceCamera : public Camera, public DeviceExportable {
+public:
+    glm::vec3 position, direction, right, up; // the same public fields
+    DeviceCamera(glm::vec3 position, glm::vec3 direction, glm::vec3 up_hint = glm::vec3(0, 0, 1));
+    std::pair<glm::vec3, glm::vec3> sampleRay(float x, float y) const override;
+    void exportTo(SceneBuilder& b) const override;
+
+private:
+    mutable std::shared_ptr<DeviceContext> ctx_;
+};
+
+// ---- RenderPlane: GridRenderPlane (src/GridRenderPlane.h:8-19) on the device --------------------------------
+class DevicePlane : public RenderPlane {
+public:
+    std::vector<float> pixels;           // filled by download(): running mean per cell
+    std::vector<size_t> pixel_counters;
+    size_t width, height;
+    float max_value = 0;
+    uint32_t plane_mode = IPT_PLANE_GRID;
+
+    DevicePlane(size_t width, size_t height);
+    ~DevicePlane();
+    void addRay(float x, float y, float value) override; // one sample -> the device accumulators
+    void download();                                     // refresh pixels / pixel_counters / max_value
+    void sums(std::vector<float>& sum, std::vector<float>& sumsq, std::vector<uint32_t>& count);
+
+    // used by render_sample: (re)attach to the device context of the scene being rendered
+    ipt_plane* attach(const std::shared_ptr<DeviceContext>& ctx);
+
+private:
+    std::shared_ptr<DeviceContext> ctx_;
+    ipt_plane* plane_ = nullptr;
+};
+
+// ---- Scene factory: sample_scenes.h:6-11 + the benchmark scenes -------------------------------------------
+Scene make_scene(const char* name); // "box", "fractal", "smallpt", "square", "corner", "openspheres", "cornell", "mesh:<n>", "lightgrid:<r>x<c>"
+inline Scene make_scene_box() { return make_scene("box"); }
+inline Scene make_scene_fractal() { return make_scene("fractal"); }
+inline Scene make_scene_smallpt() { return make_scene("smallpt"); }
+inline Scene make_scene_square_lit_by_square() { return make_scene("square"); }
+inline Scene make_scene_lit_corner() { return make_scene("corner"); }
+
+// ---- the hot path ------------------------------------------------------------------------------------------
+// params.pass_count calls of the reference's render_sample(scene, r_plane, stats) (src/main.cpp:186-223).
+// Every Scene member must be DeviceExportable (dynamic_cast, the reference's own idiom: gui.cpp:58, ddf.cpp:177);
+// otherwise this throws -- it never falls back to tracing on the CPU.
+// A DevicePlane receives the accumulators directly. Any other RenderPlane receives ONE addRay(x_centre, y_centre,
+// mean) per cell (documented approximation: `count` samples collapse into one call).
+ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, int device = 0);
+
+} // namespace ipt_b200

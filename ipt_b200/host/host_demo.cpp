@@ -1,0 +1,66 @@
+// host_demo.cpp — exercises the reference-facing C++ classes (device_plugins.hpp) end to end:
+//   scene = ipt_b200::make_scene_box();  ipt_b200::render_sample(scene, plane, params);
+// into (a) a DevicePlane and (b) a foreign RenderPlane written like the reference's GridRenderPlane, plus single-ray
+// calls through the Geometry / Lighting / Camera virtuals. Prints one JSON object; tests/test_gpu_host_cpp.py checks it.
+#include "device_plugins.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+
+// a RenderPlane the library knows nothing about: GridRenderPlane::addRay's arithmetic (src/GridRenderPlane.cpp:61-75)
+struct ForeignGridPlane : public RenderPlane {
+    std::vector<float> pixels;
+    std::vector<size_t> counters;
+    size_t width, height;
+    ForeignGridPlane(size_t w, size_t h) : pixels(w * h), counters(w * h), width(w), height(h) {}
+    void addRay(float x, float y, float value) override {
+        size_t xi = x * width;
+        size_t yi = height - y * height - 1;
+        pixels[yi * width + xi] = (pixels[yi * width + xi] * counters[yi * width + xi] + value) / (counters[yi * width + xi] + 1);
+        ++counters[yi * width + xi];
+    }
+};
+
+int main(int argc, char** argv) {
+    const char* name = argc > 1 ? argv[1] : "box";
+    int passes = argc > 2 ? atoi(argv[2]) : 4;
+    try {
+        Scene scene = ipt_b200::make_scene(name);
+        ipt_render_params p;
+        ipt_render_params_default(&p);
+        p.width = p.height = 96;
+        p.pass_count = passes;
+        ipt_b200::DevicePlane dplane(96, 96);
+        ipt_render_stats st = ipt_b200::render_sample(scene, dplane, p);
+        dplane.download();
+        double mean_d = 0;
+        size_t cnt_d = 0;
+        for (size_t i = 0; i < dplane.pixels.size(); ++i) { mean_d += (double)dplane.pixels[i] * dplane.pixel_counters[i]; cnt_d += dplane.pixel_counters[i]; }
+        ForeignGridPlane fplane(96, 96);
+        ipt_b200::render_sample(scene, fplane, p);
+        double mean_f = 0;
+        size_t cells_f = 0;
+        for (size_t i = 0; i < fplane.pixels.size(); ++i) if (fplane.counters[i]) { mean_f += fplane.pixels[i]; ++cells_f; }
+        // the virtuals, one ray at a time
+        auto ray = scene.camera->sampleRay(0.5f, 0.3f);
+        auto si = scene.geometry->traceRay(ray.first, ray.second);
+        auto li = scene.lighting->traceRayToLight(glm::vec3(0.2f, -0.8f, -1.0f), glm::vec3(0, 0, 1));
+        float sdf_up = si ? si->sdf->value(si->normal) : -1.0f;
+        glm::vec3 smp = si ? si->sdf->sample() : glm::vec3();
+        auto lddf = scene.lighting->distributionInPoint(glm::vec3(0.2f, -0.8f, -1.0f));
+        float lval = lddf->value(glm::vec3(0, 0, 1));
+        dplane.addRay(0.5f, 0.5f, 1.0f);
+        printf("{\"scene\": \"%s\", \"paths\": %llu, \"rays\": %llu, \"mean_device_plane\": %.9g, \"count_device_plane\": %zu, "
+               "\"mean_foreign_plane\": %.9g, \"cells_foreign_plane\": %zu, \"hit\": %d, \"hit_pos\": [%.9g, %.9g, %.9g], "
+               "\"hit_normal\": [%.9g, %.9g, %.9g], \"sdf_value_at_normal\": %.9g, \"sdf_sample_dot_normal\": %.9g, \"light_hit\": %d, "
+               "\"light_power\": %.9g, \"light_ddf_value\": %.9g}\n",
+               name, (unsigned long long)st.paths, (unsigned long long)st.rays, mean_d / (cnt_d ? cnt_d : 1), cnt_d, mean_f / (cells_f ? cells_f : 1),
+               cells_f, si ? 1 : 0, si ? si->position.x : 0, si ? si->position.y : 0, si ? si->position.z : 0, si ? si->normal.x : 0,
+               si ? si->normal.y : 0, si ? si->normal.z : 0, sdf_up, si ? smp.x * si->normal.x + smp.y * si->normal.y + smp.z * si->normal.z : 0,
+               li ? 1 : 0, li ? li->surface_power : 0, lval);
+    } catch (const ipt_b200::Error& e) {
+        printf("{\"error\": \"%s\", \"code\": %d}\n", e.what(), e.code);
+        return e.code == IPT_ERR_NO_DEVICE ? 3 : 1;
+    }
+    return 0;
+}

@@ -1,0 +1,62 @@
+"""The reference-facing C++ host classes (ipt_b200/host/device_plugins.hpp): build check on CPU, behaviour on the GPU."""
+import json
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HOST = ROOT / "ipt_b200" / "host"
+
+
+@pytest.fixture(scope="module")
+def host_demo(lib):
+    subprocess.run(["make", "-C", str(HOST), "check"], check=True, capture_output=True)
+    return HOST / "host_demo"
+
+
+def test_host_classes_build_and_refuse_to_run_without_a_device(host_demo, has_gpu):
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    r = subprocess.run([str(host_demo)], capture_output=True, text=True)
+    out = json.loads(r.stdout)
+    assert r.returncode == 3 and "no CPU fallback" in out["error"]
+
+
+def test_host_classes_compile_against_the_reference_headers():
+    if not Path("/root/reference/src/tracer_interfaces.h").exists():
+        pytest.skip("no reference sources here")
+    r = subprocess.run(["make", "-C", str(HOST), "check-reference"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "compile against the reference's own tracer_interfaces.h" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["box", "cornell"])
+def test_render_sample_through_the_cpp_interfaces(scene, host_demo, oracle):
+    import oracle_lib
+    from ipt_b200 import capi
+
+    r = subprocess.run([str(host_demo), scene, "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout)
+    assert out["paths"] == 96 * 96 * 4 and out["rays"] > out["paths"]
+    sd = capi.SceneDescription(scene)
+    p = capi.default_params(width=96, height=96, pass_count=4)
+    o = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 0)
+    mean = o["sum"].sum() / o["counters"].sum()
+    assert out["count_device_plane"] == 96 * 96 * 4
+    assert abs(out["mean_device_plane"] - mean) < 0.02 * mean          # same Philox stream; ulp-level flips only
+    assert abs(out["mean_foreign_plane"] * out["cells_foreign_plane"] / (96 * 96) - mean) < 0.05 * mean
+    # single-ray virtuals against the oracle
+    co, cd = oracle.camera_rays(sd.ptr, np.array([[0.5, 0.3]], np.float32))
+    t = oracle.trace_batch(sd.ptr, co, cd)
+    assert out["hit"] == 1
+    assert np.allclose(out["hit_pos"], t["pos"][0], atol=0) and np.allclose(out["hit_normal"], t["normal"][0], atol=0)
+    assert abs(out["sdf_value_at_normal"] - 1 / np.pi) < 1e-6 or scene == "cornell"
+    assert out["sdf_sample_dot_normal"] >= 0
+    assert out["light_hit"] in (0, 1)
+    lv = oracle.light_ddf_value(sd.ptr, [0.2, -0.8, -1.0], [[0, 0, 1]])[0]
+    assert abs(out["light_ddf_value"] - lv) <= 1e-4 * max(lv, 1e-6)
