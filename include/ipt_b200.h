@@ -122,7 +122,12 @@ enum ipt_plane_mode {
 
 enum ipt_render_flags {
     IPT_FLAG_TIME_KERNELS = 1u, /* bracket every kernel with CUDA events on the render stream -> ipt_render_stats::ms_* */
-    IPT_FLAG_KEEP_ZERO_WEIGHT = 2u /* trace children whose weight is exactly 0 (the reference does, main.cpp:177) */
+    IPT_FLAG_KEEP_ZERO_WEIGHT = 2u, /* trace children whose weight is exactly 0 (the reference does, main.cpp:177) */
+    IPT_FLAG_DEBUG_PRINT = 4u,      /* device printf of every ray / sample (single-path debugging) */
+    /* At the last traced depth a ray only matters if it reaches a light, so by default the geometry is intersected
+     * only for rays that hit a light ("shadow ray"); with this flag every last-level ray is resolved into
+     * surface hit / miss as well, which only affects ipt_render_stats::surface_hits / misses. */
+    IPT_FLAG_RESOLVE_LAST_LEVEL = 8u
 };
 
 typedef struct ipt_render_params {
@@ -141,7 +146,7 @@ typedef struct ipt_render_stats {
     uint64_t paths;                    /* camera samples == addRay calls */
     uint64_t rays;                     /* traced segments (Geometry::traceRay + Lighting::traceRayToLight pairs) */
     uint64_t rays_at_depth[IPT_MAX_DEPTH];
-    uint64_t surface_hits, light_hits, misses;
+    uint64_t surface_hits, light_hits, misses; /* last-level rays without a light along them are in neither (see flags) */
     uint64_t failed_samples;           /* zero-vector samples (lighting.cpp:55-56); still in the 1/n divisor */
     uint64_t zero_weight_pruned;       /* children with weight exactly 0 that were not traced */
     uint64_t nonfinite_dropped;        /* non-finite weights/values dropped (main.cpp:175,181,215) */

@@ -261,7 +261,7 @@ static int flatten_prims(const ipt_scene_desc* d, std::vector<DevPrim>& out, boo
         o.radius = p.radius;
         o.kind = p.kind;
         o.material = p.material;
-        o.curvature = p.curvature;
+        o.r2 = p.radius * p.radius;
         o.flags = p.flip_normal ? 8u : 0u;
         if (p.material >= d->n_materials) return fail(IPT_ERR_INVALID, "primitive material index out of range");
         if (p.kind == IPT_PRIM_BOX_PLANE) {
@@ -404,6 +404,25 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     for (uint32_t i = 0; i < desc->n_prims && i < IPT_INLINE_PRIMS; ++i) dv.prims[i] = prims[i];
     for (uint32_t i = 0; i < desc->n_lights && i < IPT_INLINE_LIGHTS; ++i) dv.lights[i] = lights[i];
     for (uint32_t i = 0; i < desc->n_materials && i < IPT_INLINE_MATS; ++i) dv.mats[i] = mats[i];
+    // group the box planes by (axis, sign) for the branch-free plane test
+    dv.planes_grouped = 1;
+    dv.n_planes = 0;
+    for (int k = 0; k < 6; ++k) dv.plane_of[k] = IPT_NO_HIT;
+    for (uint32_t i = 0; i < desc->n_prims; ++i)
+        if (prims[i].kind == IPT_PRIM_BOX_PLANE) {
+            uint32_t slot = 2 * (prims[i].flags & 3u) + ((prims[i].flags & 4u) ? 1u : 0u);
+            if (dv.plane_of[slot] != IPT_NO_HIT) dv.planes_grouped = 0; // duplicate plane: keep the generic ordered scan
+            dv.plane_of[slot] = i;
+            ++dv.n_planes;
+        }
+    dv.n_others = 0;
+    dv.others_inline = 1;
+    for (uint32_t i = 0; i < desc->n_prims; ++i) {
+        if (prims[i].kind == IPT_PRIM_BOX_PLANE) continue;
+        if (prims[i].kind != IPT_PRIM_SPHERE || dv.n_others == IPT_INLINE_OTHERS) { dv.others_inline = 0; break; }
+        DevSphere& sp = dv.others[dv.n_others++];
+        sp.cx = prims[i].px; sp.cy = prims[i].py; sp.cz = prims[i].pz; sp.r2 = prims[i].r2; sp.index = i;
+    }
     set_camera(dv, desc->camera);
     s->smallpt = smallpt;
     s->mesh = desc->n_triangles > 0;

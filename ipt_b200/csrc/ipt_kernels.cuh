@@ -132,20 +132,28 @@ template <bool SMALLPT, bool MESH>
 __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc);
 
 // ---- nearest light (CollectionLighting::traceRayToLight, src/CollectionLighting.cpp:23-34) -----------
-template <class LightAt>
-__device__ __forceinline__ bool trace_lights(uint32_t n, LightAt at, f3 o, f3 d, uint32_t& which, f3& lpos) {
+template <class LightRef>
+__device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f3 o, f3 d, bool& any, float& best_len, uint32_t& which, f3& lpos) {
+    LightHit e = light_trace(L, o, d);
+    if (!e.hit) return;
+    float len = xlength3(xsub3(e.position, o));
+    if (!any || best_len > len) {
+        any = true;
+        best_len = len;
+        which = i;
+        lpos = e.position;
+    }
+}
+// nearest light, scanning in list order with strict `>` (CollectionLighting.cpp:23-34)
+__device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos) {
     bool any = false;
     float best_len = 0.0f;
-    for (uint32_t i = 0; i < n; ++i) {
-        LightHit e = light_trace(at(i), o, d);
-        if (!e.hit) continue;
-        float len = xlength3(xsub3(e.position, o));
-        if (!any || best_len > len) {
-            any = true;
-            best_len = len;
-            which = i;
-            lpos = e.position;
-        }
+    if (S.light_inline) {
+#pragma unroll
+        for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
+            if (i < (int)S.n_lights) trace_one_light(S.lights[i], i, o, d, any, best_len, which, lpos);
+    } else {
+        for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light(S.lights_g[i], i, o, d, any, best_len, which, lpos);
     }
     return any;
 }
@@ -164,9 +172,7 @@ __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, Tr
     r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
-    bool lh;
-    if (S.light_inline) lh = trace_lights(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights[i]; }, o, d, r.light, r.light_pos);
-    else lh = trace_lights(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights_g[i]; }, o, d, r.light, r.light_pos);
+    bool lh = trace_lights(S, o, d, r.light, r.light_pos);
     bool sh = r.surf.prim != IPT_NO_HIT;
     r.kind = 0;
     if (lh) {
@@ -181,6 +187,30 @@ __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, Tr
     return r;
 }
 
+// Last traced depth: children of this level are never traced (main.cpp:100-101), so the ray matters only if it reaches
+// a light before any surface. Lights are tested first and the geometry only for rays that hit one ("shadow ray"):
+// the decision is the same expression as in trace_scene, evaluated for fewer rays. kind 3 = no light along the ray
+// (surface or miss, not resolved).
+template <bool SMALLPT, bool MESH>
+__device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
+    Outcome r;
+    r.light = IPT_NO_HIT;
+    r.light_pos = mk3(0, 0, 0);
+    r.surf.prim = IPT_NO_HIT; r.surf.t = IPT_INF; r.surf.tri_pos = IPT_NO_HIT;
+    bool lh = trace_lights(S, o, d, r.light, r.light_pos);
+    r.kind = 3;
+    if (!lh) return r;
+    r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
+    bool sh = r.surf.prim != IPT_NO_HIT;
+    bool light_wins = !sh;
+    if (sh) {
+        f3 sp = xpoint(o, d, r.surf.t);
+        light_wins = xlength3(xsub3(sp, o)) > xlength3(xsub3(r.light_pos, o));
+    }
+    r.kind = light_wins ? 2u : 1u;
+    return r;
+}
+
 __device__ __forceinline__ void flush_stat(unsigned long long* stats, int slot, uint32_t v) {
     // warp reduce, then one atomic per warp
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
@@ -190,7 +220,7 @@ __device__ __forceinline__ void flush_stat(unsigned long long* stats, int slot, 
 // K2 extend: one thread per ray of depth `depth`. Light hits are accumulated here (the emission is the leaf
 // of the estimator tree); surface hits are compacted into the hit queue unless this is the last traced depth.
 template <bool SMALLPT, bool MESH, bool LAST>
-__global__ void __launch_bounds__(256) k_extend(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+__global__ void __launch_bounds__(256, 4) k_extend(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -207,7 +237,8 @@ __global__ void __launch_bounds__(256) k_extend(const __grid_constant__ DevScene
             ro = C.ray_o[i];
             rd = C.ray_d[i];
             f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
-            oc = trace_scene<SMALLPT, MESH>(S, o, d, tc);
+            if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) oc = trace_scene_last<SMALLPT, MESH>(S, o, d, tc);
+            else oc = trace_scene<SMALLPT, MESH>(S, o, d, tc);
             if (C.flags & 4u)
                 printf("GPU extend d=%u node=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) thr=%.9g kind=%u prim=%u t=%.9g\n", depth,
                        C.slot_bits == 32 ? 0u : (__float_as_uint(rd.w) >> C.slot_bits), o.x, o.y, o.z, d.x, d.y, d.z, ro.w, oc.kind, oc.surf.prim, oc.surf.t);
@@ -220,7 +251,7 @@ __global__ void __launch_bounds__(256) k_extend(const __grid_constant__ DevScene
             } else if (oc.kind == 1) {
                 ++n_surface;
                 emit = !LAST;
-            } else {
+            } else if (oc.kind == 0) {
                 ++n_miss;
             }
         }
@@ -260,7 +291,12 @@ __device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, 
         material = S.tri_material;
         return;
     }
-    DevPrim p = S.prim_inline ? S.prims[prim] : S.prims_g[prim];
+    // the index differs per lane: a constant-bank read would serialise, a global (L1-cached) read does not
+    const float4* pp = reinterpret_cast<const float4*>(&S.prims_g[prim]);
+    float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+    DevPrim p;
+    p.px = p0.x; p.py = p0.y; p.pz = p0.z; p.radius = p0.w;
+    p.kind = __float_as_uint(p1.x); p.material = __float_as_uint(p1.y); p.flags = __float_as_uint(p1.z); p.r2 = p1.w;
     material = p.material;
     if (p.kind == IPT_PRIM_BOX_PLANE) {
         normal = mk3(-p.px, -p.py, -p.pz);
@@ -272,7 +308,7 @@ __device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, 
 
 // K3 shade: one thread per surface hit; spawns schedule[depth] children from the 1:1 mixture of the light DDF
 // and the surface DDF (main.cpp:142-177) and appends the survivors to the ray queue of depth+1.
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+__global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth + 1];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -304,7 +340,10 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DevScene 
             f3 normal;
             uint32_t material;
             surface_frame(S, b.y, pos, normal, material);
-            DevMaterial m = material < IPT_INLINE_MATS ? S.mats[material] : S.mats_g[material];
+            const float4* mp = reinterpret_cast<const float4*>(&S.mats_g[material]);
+            float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+            DevMaterial m;
+            m.ddf = __float_as_uint(m0.x); m.albedo = m0.y; m.wd = m0.z; m.ws = m0.w; m.exponent = m1.x;
             albedo = m.albedo;
             f3 din = mk3(0, 0, 0);
             if (m.ddf == IPT_DDF_GLOSSY) din = oct_decode(__uint_as_float(b.z), __uint_as_float(b.w)); // only the glossy lobe needs it
@@ -325,7 +364,7 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DevScene 
                 } else {
                     float sv = sdf_value(sdf, w);
                     float mv = mix_value(S, sdf, pos, w, sv);
-                    float mult = sv / mv;
+                    float mult = __fdividef(sv, mv);
                     wgt = thr * (mult * albedo) * inv_n;
                     if (C.flags & 4u)
                         printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) w=(%.9g %.9g %.9g) sv=%.9g mv=%.9g\n", depth, child, u01(r.x), u01(r.y), u01(r.z), w.x, w.y, w.z, sv, mv);

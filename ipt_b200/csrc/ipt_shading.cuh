@@ -44,23 +44,35 @@ __device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y
 
 // Base DDFs in their own frame. kind: 0 Spherical (ddf.cpp:58-72), 1 UpperHalf (:74-89), 2 Cosine (:91-108),
 // >=3 PowerCosine(kind) (extension, oracle/ref_driver.cpp).
+// z^n for a small non-negative integer n by square-and-multiply (the glossy lobe's exponent is an integer >= 3)
+__device__ __forceinline__ float ipow(float z, int n) {
+    float r = 1.0f, b = z;
+    while (n) {
+        if (n & 1) r *= b;
+        b *= b;
+        n >>= 1;
+    }
+    return r;
+}
 __device__ __forceinline__ f3 base_sample(int kind, float u1, float u2) {
     float zc;
     if (kind == 0) zc = u1 * 2.0f - 1.0f;
     else if (kind == 1) zc = u1;
     else if (kind == 2) zc = sqrtf(u1);
-    else zc = powf(u1, 1.0f / ((float)kind + 1.0f));
+    else zc = exp2f(__log2f(u1) * (1.0f / ((float)kind + 1.0f))); // u1^(1/(n+1)); u1 = 0 -> 0
     float r = sqrtf(fmaxf(0.0f, 1.0f - zc * zc));
-    float sp, cp;
-    sincospif(2.0f * u2, &sp, &cp);
+    // phi = 2*pi*u2 = pi*a + pi with a in [-1,1): cos(phi) = -cos(pi*a), sin(phi) = -sin(pi*a); the SFU sine/cosine are
+    // accurate to ~4e-7 absolute on [-pi, pi], far below the sampling noise
+    float a = (2.0f * u2 - 1.0f) * IPT_PI_F;
+    float sp = -__sinf(a), cp = -__cosf(a);
     return mk3(r * cp, r * sp, zc);
 }
 __device__ __forceinline__ float base_value(int kind, float z) {
     if (kind == 0) return 0.25f / IPT_PI_F;
     if (z < 0.0f) return 0.0f;
     if (kind == 1) return 0.5f / IPT_PI_F;
-    if (kind == 2) return z / IPT_PI_F;
-    return ((float)kind + 1.0f) * powf(z, (float)kind) / (2.0f * IPT_PI_F);
+    if (kind == 2) return z * (1.0f / IPT_PI_F);
+    return ((float)kind + 1.0f) * ipow(z, kind) * (0.5f / IPT_PI_F);
 }
 
 // The surface DDF of a hit: RotateDdf(CosineDdf, normal) or the glossy extension.
@@ -108,7 +120,7 @@ __device__ __forceinline__ float light_pdf(const DevLight& L, f3 pos, f3 w) {
     float inv = rsqrtf(decay);
     float cosinus = -(h.normal.x * dp.x + h.normal.y * dp.y + h.normal.z * dp.z) * inv;
     if (cosinus < 0.0f) return 0.0f;
-    return decay / cosinus / L.area;
+    return __fdividef(decay, cosinus * L.area);
 }
 
 // DdfFromLight::sample (src/lighting/lighting.cpp:50-59) over Light::sample (lighting.cpp:93-104, 172-207)
@@ -140,33 +152,36 @@ __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float 
     return dir;
 }
 
-template <class LightAt>
-__device__ __forceinline__ float lights_pdf(uint32_t n, LightAt at, f3 pos, f3 w) {
-    float res = 0.0f;
-    for (uint32_t i = 0; i < n; ++i) {
-        const DevLight& L = at(i);
-        res += L.weight * light_pdf(L, pos, w);
-    }
-    return res;
-}
-
 // UnionDdf::value over [lights..., sdf] (src/libddf/ddf.cpp:156-162) with the weights of main.cpp:143
 __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3 pos, f3 w, float sdf_val) {
-    float lp;
-    if (S.light_inline) lp = lights_pdf(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights[i]; }, pos, w);
-    else lp = lights_pdf(S.n_lights, [&S](uint32_t i) -> const DevLight& { return S.lights_g[i]; }, pos, w);
+    float lp = 0.0f;
+    if (S.light_inline) {
+#pragma unroll
+        for (int i = 0; i < IPT_INLINE_LIGHTS; ++i)
+            if (i < (int)S.n_lights) lp += S.lights[i].weight * light_pdf(S.lights[i], pos, w);
+    } else {
+        for (uint32_t i = 0; i < S.n_lights; ++i) {
+            const DevLight& L = S.lights_g[i];
+            lp += L.weight * light_pdf(L, pos, w);
+        }
+    }
     return lp + S.sdf_weight * sdf_val;
 }
 
-// UnionDdf::sample (src/libddf/ddf.cpp:138-154): scan the running float sum of weights with one draw.
-// r >= total (float rounding; uninitialised result in the reference) is a failed sample.
+// UnionDdf::sample (src/libddf/ddf.cpp:138-154): scan the running float sum of weights with one draw `us`; the first
+// component whose running sum exceeds it is sampled. r >= total (float rounding; uninitialised result in the
+// reference) is a failed sample. Both candidate directions are formed by every lane (no light-vs-sdf divergence).
 __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, f3 pos, float us, float u1, float u2, float ul) {
+    f3 wl = mk3(0, 0, 0);
     float acc = 0.0f;
+    bool from_light = false;
     if (S.light_inline) {
-        for (uint32_t i = 0; i < S.n_lights; ++i) {
-            acc = S.lights[i].cdf;
-            if (us < acc) return light_sample_dir(S.lights[i], pos, u1, u2);
-        }
+#pragma unroll
+        for (int i = 0; i < IPT_INLINE_LIGHTS; ++i)
+            if (i < (int)S.n_lights) {
+                acc = S.lights[i].cdf;
+                if (!from_light && us < acc) { from_light = true; wl = light_sample_dir(S.lights[i], pos, u1, u2); }
+            }
     } else if (S.n_lights) {
         // first i with us < cdf[i]; cdf is non-decreasing, so a binary search finds what the linear scan finds
         uint32_t lo = 0, hi = S.n_lights;
@@ -174,11 +189,13 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
             uint32_t mid = (lo + hi) >> 1;
             if (us < S.lights_g[mid].cdf) hi = mid; else lo = mid + 1;
         }
-        if (lo < S.n_lights) return light_sample_dir(S.lights_g[lo], pos, u1, u2);
+        if (lo < S.n_lights) { from_light = true; wl = light_sample_dir(S.lights_g[lo], pos, u1, u2); }
         acc = S.lights_g[S.n_lights - 1].cdf;
     }
+    f3 ws = sdf_sample(sdf, bn, u1, u2, ul);
+    if (from_light) return wl;
     acc += S.sdf_weight;
-    if (us < acc) return sdf_sample(sdf, bn, u1, u2, ul);
+    if (us < acc) return ws;
     return mk3(0, 0, 0);
 }
 

@@ -117,8 +117,30 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
     double dist_d = (double)IPT_INF;
     float dist_f = IPT_INF;
     uint32_t best = IPT_NO_HIT;
-    if (S.prim_inline) trace_prim_list<SMALLPT>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims[i]; }, o, d, dist_d, dist_f, best);
-    else trace_prim_list<SMALLPT>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims_g[i]; }, o, d, dist_d, dist_f, best);
+    if (!SMALLPT && S.planes_grouped) {
+        if (S.n_planes) {
+            isect_axis_planes(S.plane_of[0], S.plane_of[1], o.x, d.x, o, d, dist_f, best);
+            isect_axis_planes(S.plane_of[2], S.plane_of[3], o.y, d.y, o, d, dist_f, best);
+            isect_axis_planes(S.plane_of[4], S.plane_of[5], o.z, d.z, o, d, dist_f, best);
+        }
+        if (S.others_inline) {
+            // static indices: every sphere constant is an immediate constant-bank operand, no indexed LDC
+#pragma unroll
+            for (int k = 0; k < IPT_INLINE_OTHERS; ++k) {
+                if (k < (int)S.n_others) {
+                    const DevSphere& sp = S.others[k];
+                    float t = isect_sphere(sp.r2, xsub3(o, mk3(sp.cx, sp.cy, sp.cz)), d);
+                    if (t < dist_f || (t == dist_f && t != IPT_INF && sp.index < best)) { dist_f = t; best = sp.index; }
+                }
+            }
+        } else if (S.n_prims > S.n_planes) {
+            if (S.prim_inline) trace_prim_list<false, true>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims[i]; }, o, d, dist_d, dist_f, best);
+            else trace_prim_list<false, true>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims_g[i]; }, o, d, dist_d, dist_f, best);
+        }
+    } else {
+        if (S.prim_inline) trace_prim_list<SMALLPT, false>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims[i]; }, o, d, dist_d, dist_f, best);
+        else trace_prim_list<SMALLPT, false>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims_g[i]; }, o, d, dist_d, dist_f, best);
+    }
     SurfHit r;
     r.prim = best;
     r.tri_pos = IPT_NO_HIT;
