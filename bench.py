@@ -338,7 +338,7 @@ def run_ours(args):
             "config": {"workload": workload_text(), "passes_per_step": pps, "paths_per_step_per_gpu": W * H * pps,
                        "parallelism": f"pass-sharded x{world}" if world > 1 else "single GPU",
                        "l2": "per-step ray/hit queue working set (>1 GB) exceeds the 126 MB L2; no flush needed",
-                       "batch_paths": args.batch_paths or (1 << 18)},
+                       "batch_paths": args.batch_paths or (1 << 19)},
             "mrays_per_s": rays_all / elapsed / 1e6, "rays_per_path": rays_all / max(paths_all, 1), "image_mean": image_mean,
             "device_ms_per_step": agg["ms_dev"] / args.steps,
             "clocks": clocks,

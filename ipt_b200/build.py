@@ -61,5 +61,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """A tuning variant of the same sources: ipt_b200/lib/variants/<name>.so built with extra -D flags."""
+    out = PKG / "lib" / "variants" / f"{name}.so"
+    out.parent.mkdir(parents=True, exist_ok=True)
+    srcs = [str(s) for s in SOURCES if s.exists()]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], f"-I{ROOT / 'include'}", f"-I{PKG / 'host'}", f"-I{PKG / 'host' / 'compat'}", "-o", str(out), *srcs]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(res.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -17,7 +17,10 @@ FLAG_TIME_KERNELS, FLAG_KEEP_ZERO_WEIGHT, FLAG_DEBUG_PRINT, FLAG_RESOLVE_LAST_LE
 STATUS = {0: "IPT_OK", 1: "IPT_ERR_INVALID", 2: "IPT_ERR_CUDA", 3: "IPT_ERR_NO_DEVICE", 4: "IPT_ERR_UNSUPPORTED", 5: "IPT_ERR_OVERFLOW"}
 IPT_ERR_NO_DEVICE = 3
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libipt_b200.so"
+import os
+
+# IPT_B200_LIB selects another build of the SAME sources (kernel tuning experiments); never a different implementation
+LIB_PATH = Path(os.environ.get("IPT_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libipt_b200.so")
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)

@@ -786,7 +786,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     while ((1ull << idx_bits) < max_ray_w) ++idx_bits;
     uint32_t slot_bits = 32 - idx_bits;
     uint64_t total_paths = (uint64_t)tw * th * p->pass_count;
-    uint64_t batch = p->batch_paths ? p->batch_paths : (1u << 18);
+    uint64_t batch = p->batch_paths ? p->batch_paths : (1u << 19);
     batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
     const uint64_t budget = 24ull << 30; // bytes of queue memory
     while (batch > 1024 && batch * (max_ray_w + max_hit_w) * 32 > budget) batch >>= 1;

@@ -1,0 +1,30 @@
+"""Kernel tuning sweep: builds variants of the same sources and benches each (GPU box only)."""
+import json, os, subprocess, sys
+sys.path.insert(0, '.')
+from ipt_b200 import build
+variants = {
+    "base": [],
+    "nodefer": ["IPT_DEFER_APPEND=0"],
+    "lights4": ["IPT_INLINE_LIGHTS=4"],
+    "nodefer_lights4": ["IPT_DEFER_APPEND=0", "IPT_INLINE_LIGHTS=4"],
+    "shade2": ["IPT_SHADE_MIN_BLOCKS=2"],
+    "shade4": ["IPT_SHADE_MIN_BLOCKS=4"],
+    "ext3": ["IPT_EXTEND_MIN_BLOCKS=3"],
+    "nd_s2_e3": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=2", "IPT_EXTEND_MIN_BLOCKS=3"],
+    "nd_s2_e2": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=2", "IPT_EXTEND_MIN_BLOCKS=2"],
+    "nd_s1_e3": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=1", "IPT_EXTEND_MIN_BLOCKS=3"],
+    "nd_s3_e3": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=3", "IPT_EXTEND_MIN_BLOCKS=3"],
+}
+sel = sys.argv[1].split(",") if len(sys.argv) > 1 else list(variants)
+batches = [int(b) for b in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0"])]
+for name in sel:
+    so = build.build_variant(name, variants[name])
+    for b in batches:
+        env = dict(os.environ, IPT_B200_LIB=str(so))
+        r = subprocess.run([sys.executable, "bench.py", "--steps", "12", "--warmup", "3", "--no-cpu-baseline", "--batch-paths", str(b)], env=env, capture_output=True, text=True)
+        try:
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            k = d["roofline"]["kernel_ms"]
+            print(f"{name:18s} batch {b:8d}  {d['value']:7.1f} Mpaths/s  extend {k['extend']:7.1f}  shade {k['shade']:7.1f}  sm {d['clocks']['sm_mhz']}", flush=True)
+        except Exception as e:
+            print(name, b, "failed", r.stderr[-400:])
