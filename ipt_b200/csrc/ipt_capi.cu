@@ -19,6 +19,8 @@
 
 using namespace iptd;
 
+#define IPT_CNT_WORDS (3 * IPT_MAX_DEPTH + 2) // ray counts, hit counts, persistent-kernel fetch cursors
+
 // ---------------------------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------------------------
@@ -73,6 +75,7 @@ struct ipt_scene {
     ipt_plane* host_plane = nullptr; // for ipt_render_host
     float* pinned = nullptr;         // staging for ipt_render_host
     size_t pinned_bytes = 0;
+    int grid_mesh = 0, grid_mesh_last = 0;
     int grid_generate = 0, grid_extend = 0, grid_extend_last = 0, grid_shade = 0, grid_accumulate = 0;
 };
 
@@ -438,13 +441,17 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
         dv.tri_id = s->bvh.sorted_ids;
         dv.nodes = s->bvh.nodes;
     }
-    CUDA_TRY(cudaMalloc((void**)&s->d_cnt, sizeof(uint32_t) * (2 * IPT_MAX_DEPTH + 2)));
+    CUDA_TRY(cudaMalloc((void**)&s->d_cnt, sizeof(uint32_t) * IPT_CNT_WORDS));
     CUDA_TRY(cudaMalloc((void**)&s->d_stats, sizeof(unsigned long long) * ST_COUNT));
 
     size_t sm = stack_smem(s);
     s->grid_generate = occupancy_grid(k_generate, s->sm_count, 0);
     s->grid_shade = occupancy_grid(k_shade, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
+    if (s->mesh && !s->smallpt) {
+        s->grid_mesh = occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
+        s->grid_mesh_last = occupancy_grid(k_extend_mesh<true>, s->sm_count, sm);
+    }
 #define OCC(SP, MS)                                                                          \
     s->grid_extend = occupancy_grid(k_extend<SP, MS, false>, s->sm_count, sm);               \
     s->grid_extend_last = occupancy_grid(k_extend<SP, MS, true>, s->sm_count, sm)
@@ -797,7 +804,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     RenderCtx C;
     std::memset(&C, 0, sizeof C);
     C.ray_o = s->ws.ray_o; C.ray_d = s->ws.ray_d; C.hit_a = s->ws.hit_a; C.hit_b = s->ws.hit_b; C.pathval = s->ws.pathval;
-    C.cnt = s->d_cnt; C.stats = s->d_stats;
+    C.cnt = s->d_cnt; C.fetch = s->d_cnt + (2 * IPT_MAX_DEPTH + 2); C.stats = s->d_stats;
     C.sum = plane->sum; C.sumsq = plane->sumsq; C.count = plane->count;
     C.width = p->width; C.height = p->height;
     C.tile_x0 = tx0; C.tile_y0 = ty0; C.tile_w = tw; C.tile_h = th; C.tile_pixels = tw * th;
@@ -828,7 +835,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     for (uint64_t g0 = 0; g0 < total_paths; g0 += batch, ++batches) {
         C.g0 = g0;
         C.batch = (uint32_t)std::min<uint64_t>(batch, total_paths - g0);
-        CUDA_TRY(cudaMemsetAsync(s->d_cnt, 0, sizeof(uint32_t) * (2 * IPT_MAX_DEPTH + 2), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->d_cnt, 0, sizeof(uint32_t) * IPT_CNT_WORDS, s->stream));
 #define TIMED(kind, LAUNCH)                                             \
     do {                                                                \
         if (timing) { cudaEventRecord(ev_next(), s->stream); }         \
@@ -844,6 +851,18 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
             // never launch more warps than the level can have rays
             uint64_t max_rays = (uint64_t)C.batch * width_at[d];
             int cap_blocks = (int)std::min<uint64_t>((max_rays + IPT_BLOCK - 1) / IPT_BLOCK, 1u << 30);
+            const bool persistent_mesh = s->mesh && !s->smallpt;
+            if (persistent_mesh) {
+                // mesh scenes: persistent warps that refill idle lanes from the ray queue (ipt_trace.cuh)
+                if (last) {
+                    TIMED(1, (k_extend_mesh<true><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                    break;
+                }
+                TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                int gs2 = std::max(1, std::min(s->grid_shade, cap_blocks));
+                TIMED(2, (k_shade<<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                continue;
+            }
             if (last) {
                 int g = std::max(1, std::min(s->grid_extend_last, cap_blocks));
 #define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))

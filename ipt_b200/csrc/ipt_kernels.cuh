@@ -42,6 +42,7 @@ struct RenderCtx {
     uint4* hit_b;
     float* pathval;
     uint32_t* cnt;             // [2*d] rays at depth d, [2*d+1] surface hits at depth d
+    uint32_t* fetch;           // [d] next unfetched ray of depth d (persistent mesh kernel)
     unsigned long long* stats; // StatSlot
     // accumulators
     float* sum;
@@ -324,8 +325,8 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
 __device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, f3 pos, f3& normal, uint32_t& material) {
     if (prim >= S.n_prims) {
         uint32_t k = prim - S.n_prims; // sorted triangle position
-        float4 a = __ldg(&S.tris[3 * (size_t)k]);
-        float4 b = __ldg(&S.tris[3 * (size_t)k + 1]);
+        float4 a = __ldg(&S.tris[4 * (size_t)k]);
+        float4 b = __ldg(&S.tris[4 * (size_t)k + 1]);
         normal = mk3(a.w, b.x, b.y);
         material = S.tri_material;
         return;

@@ -13,7 +13,7 @@ namespace iptd {
 
 struct LbvhDevice {
     uint32_t n = 0;
-    float4* tri_records = nullptr;       // 3 float4 per sorted triangle (see DevScene::tris)
+    float4* tri_records = nullptr;       // 4 float4 (64 B) per sorted triangle (see DevScene::tris)
     uint32_t* sorted_ids = nullptr;      // sorted position -> original index
     unsigned long long* sorted_keys = nullptr; // 63-bit Morton keys, ascending
     BvhNode* nodes = nullptr;            // n-1 internal nodes, root = 0
@@ -262,9 +262,10 @@ __global__ void k_lbvh_records(const float* __restrict__ tris, const uint32_t* _
     float i11 = xmul(xsub(xmul(m00, m22), xmul(m20, m02)), ood);
     float i21 = xmul(-xsub(xmul(m00, m21), xmul(m20, m01)), ood);
     // coord.x = i00*r.x + i10*r.y + i20*r.z ; coord.y = i01*r.x + i11*r.y + i21*r.z
-    rec[3 * (size_t)k] = make_float4(v0.x, v0.y, v0.z, nn.x);
-    rec[3 * (size_t)k + 1] = make_float4(nn.y, nn.z, i00, i10);
-    rec[3 * (size_t)k + 2] = make_float4(i20, i01, i11, i21);
+    rec[4 * (size_t)k] = make_float4(v0.x, v0.y, v0.z, nn.x);
+    rec[4 * (size_t)k + 1] = make_float4(nn.y, nn.z, i00, i10);
+    rec[4 * (size_t)k + 2] = make_float4(i20, i01, i11, i21);
+    rec[4 * (size_t)k + 3] = make_float4(__uint_as_float(ids[k]), 0.0f, 0.0f, 0.0f); // original index rides in the 64-byte record
 }
 
 static inline void lbvh_free(LbvhDevice& b) {
@@ -313,7 +314,7 @@ static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st
             std::swap(va, vb);
         }
         LB_TRY(cudaGetLastError());
-        LB_TRY(cudaMalloc((void**)&out.tri_records, 48 * (size_t)n));
+        LB_TRY(cudaMalloc((void**)&out.tri_records, 64 * (size_t)n));
         k_lbvh_records<<<blocks, 256, 0, st>>>(d_tris, out.sorted_ids, n, out.tri_records);
         if (n > 1) {
             LB_TRY(cudaMalloc((void**)&out.nodes, sizeof(BvhNode) * (size_t)(n - 1)));

@@ -42,14 +42,14 @@ __device__ __forceinline__ float slab(float lox, float loy, float loz, float hix
 
 __device__ __forceinline__ void test_triangle(const DevScene& S, uint32_t pos, f3 o, f3 d, float& best_t, uint32_t& best_orig,
                                               uint32_t& best_pos, bool best_is_tri, TraceCounters& tc) {
-    float4 a = __ldg(&S.tris[3 * (size_t)pos]);
-    float4 b = __ldg(&S.tris[3 * (size_t)pos + 1]);
-    float4 c = __ldg(&S.tris[3 * (size_t)pos + 2]);
+    f8 r0 = ldg256(&S.tris[4 * (size_t)pos]);
+    f8 r1 = ldg256(&S.tris[4 * (size_t)pos + 2]);
     ++tc.tris;
     f3 rel;
-    float t = isect_parallelogram(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), true, o, d, &rel);
+    float t = isect_parallelogram(mk3(r0.v[0], r0.v[1], r0.v[2]), mk3(r0.v[3], r0.v[4], r0.v[5]), mk3(r0.v[6], r0.v[7], r1.v[0]),
+                                  mk3(r1.v[1], r1.v[2], r1.v[3]), true, o, d, &rel);
     if (t == IPT_INF) return;
-    uint32_t orig = __ldg(&S.tri_id[pos]);
+    uint32_t orig = __float_as_uint(r1.v[4]);
     if (t < best_t || (t == best_t && best_is_tri && orig < best_orig)) {
         best_t = t;
         best_orig = orig;
@@ -76,12 +76,12 @@ __device__ __forceinline__ bool bvh_closest(const DevScene& S, f3 o, f3 d, float
     st.n = 0;
     uint32_t node = 0;
     while (true) {
-        const float4* np = reinterpret_cast<const float4*>(&S.nodes[node]);
-        float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+        f8 n0 = ldg256(&S.nodes[node]);
+        f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
         ++tc.nodes;
-        uint32_t left = __float_as_uint(q0.w), right = __float_as_uint(q1.w);
-        float tn0 = slab(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, o, inv, best_t);
-        float tn1 = slab(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, o, inv, best_t);
+        uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
+        float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], o, inv, best_t);
+        float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], o, inv, best_t);
         uint32_t next = IPT_NO_HIT;
         bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
         // leaves are intersected immediately; inner children are visited nearer-first
@@ -112,11 +112,10 @@ __device__ __forceinline__ bool bvh_closest(const DevScene& S, f3 o, f3 d, float
 
 extern __shared__ uint32_t ipt_dyn_smem[];
 
-template <bool SMALLPT, bool MESH>
-__device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
-    double dist_d = (double)IPT_INF;
-    float dist_f = IPT_INF;
-    uint32_t best = IPT_NO_HIT;
+// the ordered analytic primitive list: grouped planes + statically unrolled spheres when the scene allows, else the
+// generic ordered scan
+template <bool SMALLPT>
+__device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, double& dist_d, float& dist_f, uint32_t& best) {
     if (!SMALLPT && S.planes_grouped) {
         if (S.n_planes) {
             isect_axis_planes(S.plane_of[0], S.plane_of[1], o.x, d.x, o, d, dist_f, best);
@@ -141,6 +140,14 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
         if (S.prim_inline) trace_prim_list<SMALLPT, false>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims[i]; }, o, d, dist_d, dist_f, best);
         else trace_prim_list<SMALLPT, false>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims_g[i]; }, o, d, dist_d, dist_f, best);
     }
+}
+
+template <bool SMALLPT, bool MESH>
+__device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
+    double dist_d = (double)IPT_INF;
+    float dist_f = IPT_INF;
+    uint32_t best = IPT_NO_HIT;
+    analytic_closest<SMALLPT>(S, o, d, dist_d, dist_f, best);
     SurfHit r;
     r.prim = best;
     r.tri_pos = IPT_NO_HIT;
@@ -157,6 +164,156 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
         }
     }
     return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2 for mesh scenes: persistent warps with ray replenishment (Aila & Laine 2009). BVH traversal lengths differ by
+// orders of magnitude between the rays of a warp (measured: 2.7-4.6 active lanes of 32 in the one-ray-per-thread
+// kernel), so a lane that finishes its ray fetches the next one from the queue instead of idling until the slowest
+// lane of its warp is done. Per-ray work is split into setup (analytic primitives, and the lights at the last depth),
+// traversal steps (one BVH node each) and finalisation (decision, emission / compaction), exactly the arithmetic of
+// trace_scene / trace_scene_last.
+// ---------------------------------------------------------------------------------------------------------------
+#define IPT_REFILL_MIN 8    // fetch new rays when at least this many lanes are idle
+#define IPT_TRAV_STEPS 4    // node visits between two refill checks
+
+template <bool LAST>
+__global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+    const uint32_t n = C.cnt[2 * depth];
+    uint32_t* next = &C.fetch[depth];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t n_surface = 0, n_light = 0, n_miss = 0;
+    TraceCounters tc{0, 0};
+    bool have = false, trav = false, exhausted = false;
+    float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
+    f3 inv = mk3(0, 0, 0), lpos = mk3(0, 0, 0);
+    float a_t = IPT_INF, best_t = IPT_INF;
+    uint32_t a_prim = IPT_NO_HIT, best_orig = IPT_NO_HIT, best_pos = IPT_NO_HIT, lwhich = IPT_NO_HIT, node = 0;
+    TravStack st;
+    st.sm = ipt_dyn_smem + threadIdx.x;
+    st.n = 0;
+    while (true) {
+        // ---- replenish idle lanes
+        uint32_t idle = __ballot_sync(0xffffffffu, !have);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= IPT_REFILL_MIN)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(idle) >= n) exhausted = true;
+            uint32_t i = base + __popc(idle & lt_mask);
+            if (!have && i < n) {
+                ro = C.ray_o[i];
+                rd = C.ray_d[i];
+                f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
+                bool go = true;
+                if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) { // shadow ray: nothing to do unless a light lies along it
+                    lwhich = IPT_NO_HIT;
+                    go = trace_lights(S, o, d, lwhich, lpos);
+                }
+                if (go) {
+                    double dd = (double)IPT_INF;
+                    a_t = IPT_INF; a_prim = IPT_NO_HIT;
+                    analytic_closest<false>(S, o, d, dd, a_t, a_prim);
+                    best_t = a_t; best_orig = IPT_NO_HIT; best_pos = IPT_NO_HIT;
+                    have = true;
+                    if (S.n_tris == 1) {
+                        test_triangle(S, 0, o, d, best_t, best_orig, best_pos, false, tc);
+                        trav = false;
+                    } else {
+                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        node = 0; st.n = 0; trav = true;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- a few BVH node visits
+        for (int step = 0; step < IPT_TRAV_STEPS; ++step) {
+            if (have && trav) {
+                f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
+                f8 n0 = ldg256(&S.nodes[node]);
+                f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
+                ++tc.nodes;
+                uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
+                float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], o, inv, best_t);
+                float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], o, inv, best_t);
+                bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
+                if (h0 && (left & 0x80000000u)) { test_triangle(S, left & 0x7FFFFFFFu, o, d, best_t, best_orig, best_pos, best_orig != IPT_NO_HIT, tc); h0 = false; }
+                if (h1 && (right & 0x80000000u)) { test_triangle(S, right & 0x7FFFFFFFu, o, d, best_t, best_orig, best_pos, best_orig != IPT_NO_HIT, tc); h1 = false; }
+                uint32_t nxt = IPT_NO_HIT;
+                if (h0 && h1) {
+                    bool first0 = tn0 <= tn1;
+                    nxt = first0 ? left : right;
+                    st.push(first0 ? right : left);
+                } else if (h0) nxt = left;
+                else if (h1) nxt = right;
+                if (nxt == IPT_NO_HIT) {
+                    if (st.n == 0) trav = false;
+                    else nxt = st.pop();
+                }
+                node = nxt;
+            }
+            if (!__any_sync(0xffffffffu, have && trav)) break;
+        }
+        // ---- finalise finished rays (main.cpp:111-128), compact the survivors
+        bool fin = have && !trav;
+        bool emit = false;
+        uint32_t prim = IPT_NO_HIT, iprim = IPT_NO_HIT;
+        float t = IPT_INF;
+        if (fin) {
+            f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
+            bool tri = best_orig != IPT_NO_HIT;
+            prim = tri ? S.n_prims + best_orig : a_prim;
+            iprim = tri ? S.n_prims + best_pos : a_prim;
+            t = tri ? best_t : a_t;
+            bool lh;
+            if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) lh = true;
+            else { lwhich = IPT_NO_HIT; lh = trace_lights(S, o, d, lwhich, lpos); }
+            bool sh = prim != IPT_NO_HIT;
+            uint32_t kind = sh ? 1u : 0u;
+            if (lh) {
+                bool light_wins = !sh;
+                if (sh) light_wins = xlength3(xsub3(xpoint(o, d, t), o)) > xlength3(xsub3(lpos, o));
+                if (light_wins) kind = 2u;
+            }
+            if (kind == 2u) {
+                ++n_light;
+                float power = S.light_inline ? S.lights[lwhich].surface_power : S.lights_g[lwhich].surface_power;
+                if (!isfinite(power)) power = 1.0f;
+                atomicAdd(&C.pathval[__float_as_uint(rd.w) & C.slot_mask], ro.w * power);
+            } else if (kind == 1u) {
+                ++n_surface;
+                emit = !LAST;
+            } else {
+                ++n_miss;
+            }
+            have = false;
+        }
+        if (!LAST) {
+            uint32_t ballot = __ballot_sync(0xffffffffu, emit);
+            if (ballot) {
+                uint32_t basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&C.cnt[2 * depth + 1], (uint32_t)__popc(ballot));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (emit) {
+                    uint32_t j = basepos + __popc(ballot & lt_mask);
+                    f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), t);
+                    float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
+                    C.hit_a[j] = make_float4(p.x, p.y, p.z, ro.w);
+                    C.hit_b[j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+                }
+            }
+        }
+    }
+    flush_stat(C.stats, ST_SURFACE, n_surface);
+    flush_stat(C.stats, ST_LIGHT, n_light);
+    flush_stat(C.stats, ST_MISS, n_miss);
+    flush_stat(C.stats, ST_NODES, tc.nodes);
+    flush_stat(C.stats, ST_TRIS, tc.tris);
 }
 
 } // namespace iptd
