@@ -10,8 +10,10 @@
 
 namespace iptd {
 
+#ifndef IPT_STACK_SHORT
 #define IPT_STACK_SHORT 12  // entries per thread in shared memory
-#define IPT_STACK_LOCAL 84  // overflow entries in local memory (tree height bound: 63 key bits + 32 index bits)
+#endif
+#define IPT_STACK_LOCAL (104 - IPT_STACK_SHORT)  // overflow entries in local memory (tree height bound 63 key bits + 32 index bits, + postponed leaves)
 #define IPT_BLOCK 256
 
 struct TravStack {
@@ -174,8 +176,15 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 // traversal steps (one BVH node each) and finalisation (decision, emission / compaction), exactly the arithmetic of
 // trace_scene / trace_scene_last.
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef IPT_REFILL_MIN
 #define IPT_REFILL_MIN 8    // fetch new rays when at least this many lanes are idle
-#define IPT_TRAV_STEPS 4    // node visits between two refill checks
+#endif
+#ifndef IPT_TRAV_STEPS
+#define IPT_TRAV_STEPS 12    // node visits between two refill checks
+#endif
+#ifndef IPT_LEAF_BATCH
+#define IPT_LEAF_BATCH 10   // run the postponed triangle tests once this many lanes hold one
+#endif
 
 template <bool LAST>
 __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_const
     float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
     f3 inv = mk3(0, 0, 0), lpos = mk3(0, 0, 0);
     float a_t = IPT_INF, best_t = IPT_INF;
-    uint32_t a_prim = IPT_NO_HIT, best_orig = IPT_NO_HIT, best_pos = IPT_NO_HIT, lwhich = IPT_NO_HIT, node = 0;
+    uint32_t a_prim = IPT_NO_HIT, best_orig = IPT_NO_HIT, best_pos = IPT_NO_HIT, lwhich = IPT_NO_HIT, node = 0, pend = IPT_NO_HIT;
     TravStack st;
     st.sm = ipt_dyn_smem + threadIdx.x;
     st.n = 0;
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_const
                         trav = false;
                     } else {
                         inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                        node = 0; st.n = 0; trav = true;
+                        node = 0; pend = IPT_NO_HIT; st.n = 0; trav = true;
                     }
                 }
             }
@@ -231,31 +240,51 @@ __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_const
             if (exhausted) break;
             continue;
         }
-        // ---- a few BVH node visits
+        // ---- a few BVH node visits. Triangle tests are POSTPONED (speculative while-while traversal, Aila & Laine
+        // 2009): a hit leaf is parked in `pend` (further ones go on the stack) and lanes keep walking inner nodes;
+        // the exact triangle test then runs for many lanes at once instead of for the 1-2 lanes that happen to
+        // reach a leaf in the same step.
         for (int step = 0; step < IPT_TRAV_STEPS; ++step) {
             if (have && trav) {
-                f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
-                f8 n0 = ldg256(&S.nodes[node]);
-                f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
-                ++tc.nodes;
-                uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
-                float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], o, inv, best_t);
-                float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], o, inv, best_t);
-                bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
-                if (h0 && (left & 0x80000000u)) { test_triangle(S, left & 0x7FFFFFFFu, o, d, best_t, best_orig, best_pos, best_orig != IPT_NO_HIT, tc); h0 = false; }
-                if (h1 && (right & 0x80000000u)) { test_triangle(S, right & 0x7FFFFFFFu, o, d, best_t, best_orig, best_pos, best_orig != IPT_NO_HIT, tc); h1 = false; }
-                uint32_t nxt = IPT_NO_HIT;
-                if (h0 && h1) {
-                    bool first0 = tn0 <= tn1;
-                    nxt = first0 ? left : right;
-                    st.push(first0 ? right : left);
-                } else if (h0) nxt = left;
-                else if (h1) nxt = right;
-                if (nxt == IPT_NO_HIT) {
-                    if (st.n == 0) trav = false;
-                    else nxt = st.pop();
+                if (node != IPT_NO_HIT && pend == IPT_NO_HIT) {
+                    f3 o = mk3(ro.x, ro.y, ro.z);
+                    f8 n0 = ldg256(&S.nodes[node]);
+                    f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
+                    ++tc.nodes;
+                    uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
+                    float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], o, inv, best_t);
+                    float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], o, inv, best_t);
+                    bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
+                    if (h0 && (left & 0x80000000u)) { pend = left; h0 = false; }
+                    if (h1 && (right & 0x80000000u)) {
+                        if (pend == IPT_NO_HIT) pend = right; else st.push(right);
+                        h1 = false;
+                    }
+                    uint32_t nxt = IPT_NO_HIT;
+                    if (h0 && h1) {
+                        bool first0 = tn0 <= tn1;
+                        nxt = first0 ? left : right;
+                        st.push(first0 ? right : left);
+                    } else if (h0) nxt = left;
+                    else if (h1) nxt = right;
+                    node = nxt;
                 }
-                node = nxt;
+                if (node == IPT_NO_HIT && pend == IPT_NO_HIT) {
+                    if (st.n == 0) trav = false;
+                    else {
+                        uint32_t x = st.pop();
+                        if (x & 0x80000000u) pend = x; else node = x;
+                    }
+                }
+            }
+            uint32_t pm = __ballot_sync(0xffffffffu, have && trav && pend != IPT_NO_HIT);
+            uint32_t walk = __ballot_sync(0xffffffffu, have && trav && pend == IPT_NO_HIT);
+            if (pm && (__popc(pm) >= IPT_LEAF_BATCH || walk == 0 || step == IPT_TRAV_STEPS - 1)) {
+                if (have && trav && pend != IPT_NO_HIT) {
+                    test_triangle(S, pend & 0x7FFFFFFFu, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), best_t, best_orig, best_pos, best_orig != IPT_NO_HIT, tc);
+                    pend = IPT_NO_HIT;
+                    if (node == IPT_NO_HIT && st.n == 0) trav = false;
+                }
             }
             if (!__any_sync(0xffffffffu, have && trav)) break;
         }
