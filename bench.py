@@ -314,11 +314,11 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel and its algorithmic bytes: ray / hit records are 32 B
+        # dominant kernel and its algorithmic bytes: ray records are 36 B, hit records 32 B
         children = agg["rays"] - agg["paths"]
-        queued = (agg["queue_bytes"] - 64 * agg["rays"] - 8 * agg["paths"]) // 64
-        bytes_ext = 32 * agg["rays"] + 32 * queued + 8 * agg["light"]
-        bytes_shade = 32 * queued + 32 * children
+        queued = (agg["queue_bytes"] - 72 * agg["rays"] - 8 * agg["paths"]) // 64
+        bytes_ext = 36 * agg["rays"] + 32 * queued + 8 * agg["light"]
+        bytes_shade = 32 * queued + 36 * children
         dom = "shade" if agg["ms_shade"] >= agg["ms_ext"] else "extend"
         dom_ms = agg["ms_shade"] if dom == "shade" else agg["ms_ext"]
         dom_n = agg["n_shade"] if dom == "shade" else agg["n_ext"]

@@ -51,6 +51,7 @@ static bool check_eps_constants() {
 struct Workspace {
     float4* ray_o = nullptr;
     float4* ray_d = nullptr;
+    float* ray_x = nullptr;
     float4* hit_a = nullptr;
     uint4* hit_b = nullptr;
     float* pathval = nullptr;
@@ -462,7 +463,7 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
 }
 
 static void free_workspace(Workspace& w) {
-    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.hit_a); cudaFree(w.hit_b); cudaFree(w.pathval);
+    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.ray_x); cudaFree(w.hit_a); cudaFree(w.hit_b); cudaFree(w.pathval);
     w = Workspace();
 }
 
@@ -755,6 +756,7 @@ static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t
     free_workspace(w);
     CUDA_TRY(cudaMalloc((void**)&w.ray_o, 16 * ray_cap));
     CUDA_TRY(cudaMalloc((void**)&w.ray_d, 16 * ray_cap));
+    CUDA_TRY(cudaMalloc((void**)&w.ray_x, 4 * ray_cap));
     CUDA_TRY(cudaMalloc((void**)&w.hit_a, 16 * std::max<size_t>(hit_cap, 1)));
     CUDA_TRY(cudaMalloc((void**)&w.hit_b, 16 * std::max<size_t>(hit_cap, 1)));
     CUDA_TRY(cudaMalloc((void**)&w.pathval, 4 * path_cap));
@@ -796,14 +798,14 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     uint64_t batch = p->batch_paths ? p->batch_paths : (1u << 19);
     batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
     const uint64_t budget = 24ull << 30; // bytes of queue memory
-    while (batch > 1024 && batch * (max_ray_w + max_hit_w) * 32 > budget) batch >>= 1;
+    while (batch > 1024 && batch * (max_ray_w * 36 + max_hit_w * 32) > budget) batch >>= 1;
     batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(total_paths, 1)));
     int rc = ensure_workspace(s, batch * max_ray_w, batch * max_hit_w, batch);
     if (rc) return rc;
 
     RenderCtx C;
     std::memset(&C, 0, sizeof C);
-    C.ray_o = s->ws.ray_o; C.ray_d = s->ws.ray_d; C.hit_a = s->ws.hit_a; C.hit_b = s->ws.hit_b; C.pathval = s->ws.pathval;
+    C.ray_o = s->ws.ray_o; C.ray_d = s->ws.ray_d; C.ray_x = s->ws.ray_x; C.hit_a = s->ws.hit_a; C.hit_b = s->ws.hit_b; C.pathval = s->ws.pathval;
     C.cnt = s->d_cnt; C.fetch = s->d_cnt + (2 * IPT_MAX_DEPTH + 2); C.stats = s->d_stats;
     C.sum = plane->sum; C.sumsq = plane->sumsq; C.count = plane->count;
     C.width = p->width; C.height = p->height;
@@ -918,8 +920,8 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 }
             }
         }
-        // ray record written + read (2 x 32 B) per ray, hit record written + read per QUEUED surface hit, pathval RMW
-        stats->queue_bytes = 64ull * stats->rays + 64ull * h[ST_QUEUED] + 8ull * stats->paths;
+        // ray record written + read (2 x 36 B) per ray, hit record written + read per QUEUED surface hit, pathval RMW
+        stats->queue_bytes = 72ull * stats->rays + 64ull * h[ST_QUEUED] + 8ull * stats->paths;
     }
     return IPT_OK;
 }

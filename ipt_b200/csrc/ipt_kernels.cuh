@@ -6,7 +6,9 @@
 // ("throughput") and a light hit adds throughput * emission to its path; no tree reduction is needed.
 //
 // Queues (SoA, one 128-bit load/store per field and thread, coalesced):
-//   ray  : float4 (origin.xyz, throughput)  float4 (direction.xyz, tag)             32 B
+//   ray  : float4 (origin.xyz, K)  float4 (direction.xyz, tag)  float sv                         36 B
+//          one-light scenes: the ray's weight is K * sv / mix(direction) and the mixture density needs the light hit
+//          along the ray, which k_extend computes anyway -> the weight is resolved there (sv < 0: weight = K)
 //   hit  : float4 (position.xyz, throughput) uint4 (tag, prim, octahedral incoming direction) 32 B
 //   tag  = path slot in the batch | node index within its tree level << slot_bits
 // Live-path compaction: a ray that misses or reaches a light writes nothing; survivors are appended with a
@@ -38,6 +40,7 @@ struct RenderCtx {
     // queues
     float4* ray_o;
     float4* ray_d;
+    float* ray_x;              // sdf value of the sampled direction (weight resolution is deferred to k_extend), or -1
     float4* hit_a;
     uint4* hit_b;
     float* pathval;
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DevSce
         camera_ray(S.cam, x, y, o, d);
         C.ray_o[slot] = make_float4(o.x, o.y, o.z, 1.0f);
         C.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
+        C.ray_x[slot] = -1.0f;
         C.pathval[slot] = 0.0f;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) C.cnt[0] = C.batch;
@@ -221,6 +225,15 @@ __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 
     return r;
 }
 
+// Resolves a ray's weight (see the queue description above): K * sv / (w_light * pdf_light(dir) + w_sdf * sv), the
+// `sdf/mix` multiplier of main.cpp:172-173 with UnionDdf::value (ddf.cpp:156-162) for the one-light mixture.
+__device__ __forceinline__ float resolve_weight(const DevScene& S, float K, float sv, f3 o, bool light_hit, f3 lpos) {
+    if (sv < 0.0f) return K;
+    float lp = 0.0f;
+    if (light_hit) lp = S.lights[0].weight * light_pdf_at(S.lights[0], o, lpos);
+    return K * __fdividef(sv, lp + S.sdf_weight * sv);
+}
+
 __device__ __forceinline__ void flush_stat(unsigned long long* stats, int slot, uint32_t v) {
     // warp reduce, then one atomic per warp
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t n_surface = 0, n_light = 0, n_miss = 0;
+    uint32_t n_surface = 0, n_light = 0, n_miss = 0, n_dropped = 0;
     TraceCounters tc{0, 0};
     uint32_t pend_ballot = 0, pend_base = 0;
     bool pend_emit = false;
@@ -250,9 +263,12 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
         if (active) {
             ro = C.ray_o[i];
             rd = C.ray_d[i];
+            float sv = C.ray_x[i];
             f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
             if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) oc = trace_scene_last<SMALLPT, MESH>(S, o, d, tc);
             else oc = trace_scene<SMALLPT, MESH>(S, o, d, tc);
+            ro.w = resolve_weight(S, ro.w, sv, o, oc.light != IPT_NO_HIT, oc.light_pos);
+            if (!isfinite(ro.w)) { ++n_dropped; oc.kind = 4; } // non-finite multiplier (main.cpp:175): drop this sample
             if (C.flags & 4u)
                 printf("GPU extend d=%u node=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) thr=%.9g kind=%u prim=%u t=%.9g\n", depth,
                        C.slot_bits == 32 ? 0u : (__float_as_uint(rd.w) >> C.slot_bits), o.x, o.y, o.z, d.x, d.y, d.z, ro.w, oc.kind, oc.surf.prim, oc.surf.t);
@@ -315,6 +331,7 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
     flush_stat(C.stats, ST_SURFACE, n_surface);
     flush_stat(C.stats, ST_LIGHT, n_light);
     flush_stat(C.stats, ST_MISS, n_miss);
+    flush_stat(C.stats, ST_DROPPED, n_dropped);
     if (MESH) {
         flush_stat(C.stats, ST_NODES, tc.nodes);
         flush_stat(C.stats, ST_TRIS, tc.tris);
@@ -360,6 +377,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
     uint32_t pend_ballot = 0, pend_base = 0;
     bool pend_emit = false;
     float4 pend_o = make_float4(0, 0, 0, 0), pend_d = make_float4(0, 0, 0, 0);
+    float pend_x = -1.0f;
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
         uint32_t i = base + lane;
         bool active = i < n;
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
         for (uint32_t c = 0; c < n_children; ++c) {
             bool emit = false;
             f3 w = mk3(0, 0, 0);
-            float wgt = 0.0f;
+            float wgt = 0.0f, child_sv = -1.0f;
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
@@ -406,14 +424,25 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
                 } else {
                     float sv = sdf_value(sdf, w);
-                    float mv = mix_value(S, sdf, pos, w, sv);
-                    float mult = __fdividef(sv, mv);
-                    wgt = thr * (mult * albedo) * inv_n;
-                    if (C.flags & 4u)
-                        printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) w=(%.9g %.9g %.9g) sv=%.9g mv=%.9g\n", depth, child, u01(r.x), u01(r.y), u01(r.z), w.x, w.y, w.z, sv, mv);
-                    if (!isfinite(wgt)) ++n_dropped;
-                    else if (wgt == 0.0f && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
-                    else emit = true;
+                    if (S.light_inline) {
+                        // one-light scene: k_extend intersects that light for this ray anyway, so the mixture density
+                        // (and with it the weight K*sv/mix) is resolved there; sv == 0 already means weight 0
+                        wgt = thr * albedo * inv_n;
+                        child_sv = sv;
+                        if (!isfinite(sv)) ++n_dropped;
+                        else if (sv == 0.0f && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
+                        else emit = true;
+                    } else {
+                        float mv = mix_value(S, sdf, pos, w, sv);
+                        float mult = __fdividef(sv, mv);
+                        wgt = thr * (mult * albedo) * inv_n;
+                        child_sv = -1.0f;
+                        if (C.flags & 4u)
+                            printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) w=(%.9g %.9g %.9g) sv=%.9g mv=%.9g\n", depth, child, u01(r.x), u01(r.y), u01(r.z), w.x, w.y, w.z, sv, mv);
+                        if (!isfinite(wgt)) ++n_dropped;
+                        else if (wgt == 0.0f && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
+                        else emit = true;
+                    }
                 }
             }
             // warp-aggregated append, write deferred by one child (see k_extend)
@@ -426,6 +455,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
                     uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
                     C.ray_o[j] = pend_o;
                     C.ray_d[j] = pend_d;
+                    C.ray_x[j] = pend_x;
                 }
             }
             pend_ballot = ballot; pend_base = basepos; pend_emit = emit;
@@ -433,6 +463,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
                 uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
                 pend_o = make_float4(pos.x, pos.y, pos.z, wgt);
                 pend_d = make_float4(w.x, w.y, w.z, __uint_as_float(ctag));
+                pend_x = child_sv;
             }
 #if !IPT_DEFER_APPEND
             if (pend_ballot) {
@@ -441,6 +472,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
                     uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
                     C.ray_o[j] = pend_o;
                     C.ray_d[j] = pend_d;
+                    C.ray_x[j] = pend_x;
                 }
                 pend_ballot = 0;
             }
@@ -453,6 +485,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
             uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
             C.ray_o[j] = pend_o;
             C.ray_d[j] = pend_d;
+            C.ray_x[j] = pend_x;
         }
     }
     flush_stat(C.stats, ST_FAILED, n_failed);

@@ -123,6 +123,24 @@ __device__ __forceinline__ float light_pdf(const DevLight& L, f3 pos, f3 w) {
     return __fdividef(decay, cosinus * L.area);
 }
 
+// The same density from an already known light hit (its position on light L along the ray from `pos`): what
+// DdfFromLight::value computes after its own light->traceRay (lighting.cpp:63-72). Used by k_extend, which has just
+// intersected the lights for this very ray, so the shading kernel does not have to trace the light a second time.
+__device__ __forceinline__ float light_pdf_at(const DevLight& L, f3 pos, f3 hit) {
+    f3 dp = mk3(hit.x - pos.x, hit.y - pos.y, hit.z - pos.z);
+    float decay = dot3(dp, dp);
+    f3 n;
+    if (L.kind <= IPT_LIGHT_AREA_TRIANGLE) n = mk3(L.nx, L.ny, L.nz);
+    else {
+        float ir = 1.0f / L.radius;
+        n = mk3((hit.x - L.px) * ir, (hit.y - L.py) * ir, (hit.z - L.pz) * ir);
+        if (L.kind == IPT_LIGHT_SPHERE_INVERTED) n = neg3(n);
+    }
+    float cosinus = -dot3(n, dp) * rsqrtf(decay);
+    if (cosinus < 0.0f) return 0.0f;
+    return __fdividef(decay, cosinus * L.area);
+}
+
 // DdfFromLight::sample (src/lighting/lighting.cpp:50-59) over Light::sample (lighting.cpp:93-104, 172-207)
 __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float u1, float u2) {
     f3 p, n;

@@ -192,12 +192,12 @@ __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_const
     uint32_t* next = &C.fetch[depth];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t n_surface = 0, n_light = 0, n_miss = 0;
+    uint32_t n_surface = 0, n_light = 0, n_miss = 0, n_dropped = 0;
     TraceCounters tc{0, 0};
     bool have = false, trav = false, exhausted = false;
     float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
     f3 inv = mk3(0, 0, 0), lpos = mk3(0, 0, 0);
-    float a_t = IPT_INF, best_t = IPT_INF;
+    float a_t = IPT_INF, best_t = IPT_INF, sv = -1.0f;
     uint32_t a_prim = IPT_NO_HIT, best_orig = IPT_NO_HIT, best_pos = IPT_NO_HIT, lwhich = IPT_NO_HIT, node = 0, pend = IPT_NO_HIT;
     TravStack st;
     st.sm = ipt_dyn_smem + threadIdx.x;
@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_const
             if (!have && i < n) {
                 ro = C.ray_o[i];
                 rd = C.ray_d[i];
+                sv = C.ray_x[i];
                 f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
                 bool go = true;
                 if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) { // shadow ray: nothing to do unless a light lies along it
@@ -303,22 +304,31 @@ __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_const
             if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) lh = true;
             else { lwhich = IPT_NO_HIT; lh = trace_lights(S, o, d, lwhich, lpos); }
             bool sh = prim != IPT_NO_HIT;
-            uint32_t kind = sh ? 1u : 0u;
-            if (lh) {
-                bool light_wins = !sh;
-                if (sh) light_wins = xlength3(xsub3(xpoint(o, d, t), o)) > xlength3(xsub3(lpos, o));
-                if (light_wins) kind = 2u;
-            }
-            if (kind == 2u) {
-                ++n_light;
-                float power = S.light_inline ? S.lights[lwhich].surface_power : S.lights_g[lwhich].surface_power;
-                if (!isfinite(power)) power = 1.0f;
-                atomicAdd(&C.pathval[__float_as_uint(rd.w) & C.slot_mask], ro.w * power);
-            } else if (kind == 1u) {
-                ++n_surface;
-                emit = !LAST;
+            float K = ro.w;
+            ro.w = resolve_weight(S, ro.w, sv, o, lh, lpos);
+            if (C.flags & 4u)
+                printf("GPU mesh extend d=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) K=%.9g sv=%.9g thr=%.9g lh=%d lpos=(%.9g %.9g %.9g) prim=%u t=%.9g\n", depth, o.x, o.y, o.z,
+                       d.x, d.y, d.z, K, sv, ro.w, (int)lh, lpos.x, lpos.y, lpos.z, prim, t);
+            if (!isfinite(ro.w)) {
+                ++n_dropped; // non-finite multiplier (main.cpp:175): drop this sample
             } else {
-                ++n_miss;
+                bool light_wins = false;
+                if (lh) {
+                    float len_light = xlength3(xsub3(lpos, o));
+                    float len_surf = sh ? xlength3(xsub3(xpoint(o, d, t), o)) : IPT_INF;
+                    light_wins = !sh || len_surf > len_light; // main.cpp:113
+                }
+                if (light_wins) {
+                    ++n_light;
+                    float power = S.light_inline ? S.lights[lwhich].surface_power : S.lights_g[lwhich].surface_power;
+                    if (!isfinite(power)) power = 1.0f;
+                    atomicAdd(&C.pathval[__float_as_uint(rd.w) & C.slot_mask], ro.w * power);
+                } else if (sh) {
+                    ++n_surface;
+                    emit = !LAST;
+                } else {
+                    ++n_miss;
+                }
             }
             have = false;
         }
@@ -341,6 +351,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_const
     flush_stat(C.stats, ST_SURFACE, n_surface);
     flush_stat(C.stats, ST_LIGHT, n_light);
     flush_stat(C.stats, ST_MISS, n_miss);
+    flush_stat(C.stats, ST_DROPPED, n_dropped);
     flush_stat(C.stats, ST_NODES, tc.nodes);
     flush_stat(C.stats, ST_TRIS, tc.tris);
 }
