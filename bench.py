@@ -291,12 +291,16 @@ def run_ours(args):
     # ---- end to end through the C ABI with HOST buffers: per step camera in, sum/sumsq/count out ----
     cam = sd.desc.camera
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    # the caller's result buffers: pinned host memory, reused every step
+    host_out = (torch.empty(H * W, dtype=torch.float32).pin_memory().numpy(), torch.empty(H * W, dtype=torch.float32).pin_memory().numpy(),
+                torch.empty(H * W, dtype=torch.int32).pin_memory().numpy().view(np.uint32))
+    sc.render_host(params(args.warmup, flags=0), out=host_out)  # warm the host plane / staging path
     sync()
     t0 = time.perf_counter()
     e2e_paths = 0
     for s in range(e2e_steps):
         capi.check(lib.ipt_scene_set_camera(sc.handle, C.byref(cam)))
-        hs, hq, hc, st = sc.render_host(params(args.warmup + s, flags=0))
+        hs, hq, hc, st = sc.render_host(params(args.warmup + s, flags=0), out=host_out)
         e2e_paths += st.paths
         if world > 1:  # N GPUs: the per-rank results are merged where the user reads them
             part = torch.from_numpy(hs).cuda()

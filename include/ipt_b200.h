@@ -192,6 +192,11 @@ int ipt_camera_look(const float position[3], const float direction[3], const flo
 int ipt_trace_batch(ipt_scene* scene, const float* origins, const float* directions, size_t n, uint32_t* prim_id,
                     float* t, uint32_t* light_id, float* light_pos, uint32_t* outcome);
 
+/* ray_power_preview (src/main.cpp:55-92), the reference's alternative `ray_power` (main.cpp:53): 1 if a light is
+ * reached first, 0 on a miss, else dot(normal, -direction) / length(direction) at the first surface hit. n rays in
+ * HOST memory, one float each out. Deterministic, so it is compared bit for bit. */
+int ipt_preview_batch(ipt_scene* scene, const float* origins, const float* directions, size_t n, float* value);
+
 /* Camera::sampleRay (tracer_interfaces.h:42) for n (x,y) pairs. */
 int ipt_camera_rays(ipt_scene* scene, const float* xy, size_t n, float* origins, float* directions);
 

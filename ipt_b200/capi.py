@@ -97,6 +97,7 @@ SIGNATURES = {
     "ipt_light_derived": (C.c_int, [C.POINTER(Light), f32p, f32p, f32p]),
     "ipt_camera_look": (C.c_int, [f32p, f32p, f32p, C.POINTER(Camera)]),
     "ipt_trace_batch": (C.c_int, [_vp, f32p, f32p, C.c_size_t, u32p, f32p, u32p, f32p, u32p]),
+    "ipt_preview_batch": (C.c_int, [_vp, f32p, f32p, C.c_size_t, f32p]),
     "ipt_camera_rays": (C.c_int, [_vp, f32p, C.c_size_t, f32p, f32p]),
     "ipt_ddf_value": (C.c_int, [_vp, C.c_int, f32p, f32p, C.c_size_t, f32p]),
     "ipt_ddf_sample": (C.c_int, [_vp, C.c_int, f32p, C.c_uint64, C.c_size_t, f32p]),
@@ -226,6 +227,12 @@ class Scene:
                                      _ptr(light, u32p), _ptr(lpos, f32p), _ptr(outcome, u32p)))
         return dict(prim=prim, t=t, light=light, light_pos=lpos, outcome=outcome)
 
+    def preview_batch(self, origins, directions):
+        o, d = _f32(origins).reshape(-1, 3), _f32(directions).reshape(-1, 3)
+        v = np.empty(o.shape[0], np.float32)
+        check(load().ipt_preview_batch(self.handle, _ptr(o, f32p), _ptr(d, f32p), o.shape[0], _ptr(v, f32p)))
+        return v
+
     def camera_rays(self, xy):
         xy = _f32(xy).reshape(-1, 2)
         n = xy.shape[0]
@@ -273,10 +280,13 @@ class Scene:
         check(load().ipt_bvh_export(self.handle, nodes.ctypes.data_as(C.POINTER(BvhNode)), _ptr(order, u32p), _ptr(keys, u64p), C.byref(n_nodes)))
         return nodes, order, keys
 
-    def render_host(self, params: RenderParams):
-        """The end-to-end call: host buffers in, host buffers out."""
+    def render_host(self, params: RenderParams, out=None):
+        """The end-to-end call: host buffers in, host buffers out. `out` = (sum, sumsq, count) arrays to reuse."""
         n = params.width * params.height
-        s = np.empty(n, np.float32); q = np.empty(n, np.float32); c = np.empty(n, np.uint32)
+        if out is None:
+            s = np.empty(n, np.float32); q = np.empty(n, np.float32); c = np.empty(n, np.uint32)
+        else:
+            s, q, c = (a.reshape(-1) for a in out)
         st = RenderStats()
         check(load().ipt_render_host(self.handle, C.byref(params), _ptr(s, f32p), _ptr(q, f32p), _ptr(c, u32p), C.byref(st)))
         shape = (params.height, params.width)

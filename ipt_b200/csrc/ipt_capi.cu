@@ -107,6 +107,26 @@ __global__ void __launch_bounds__(IPT_BLOCK) k_trace_batch(const __grid_constant
     if (outcome) outcome[i] = oc.kind;
 }
 
+// ray_power_preview (src/main.cpp:55-92)
+template <bool SMALLPT, bool MESH>
+__global__ void __launch_bounds__(IPT_BLOCK) k_preview_batch(const __grid_constant__ DevScene S, const float* __restrict__ o, const float* __restrict__ d,
+                                                             size_t n, float* value) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TraceCounters tc{0, 0};
+    f3 oo = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), dd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    Outcome oc = trace_scene<SMALLPT, MESH>(S, oo, dd, tc);
+    float v = 0.0f;
+    if (oc.kind == 2) v = 1.0f;
+    else if (oc.kind == 1) {
+        f3 pos = xpoint(oo, dd, oc.surf.t), normal;
+        uint32_t material;
+        surface_frame(S, oc.surf.tri_pos != IPT_NO_HIT ? S.n_prims + oc.surf.tri_pos : oc.surf.prim, pos, normal, material);
+        v = xdiv(xdot3(normal, neg3(dd)), xlength3(dd));
+    }
+    value[i] = v;
+}
+
 __global__ void k_camera_rays(const __grid_constant__ DevScene S, const float* __restrict__ xy, size_t n, float* o, float* d) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -511,6 +531,24 @@ int ipt_trace_batch(ipt_scene* s, const float* origins, const float* directions,
     if (light_id) CUDA_TRY(cudaMemcpyAsync(light_id, d_light.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
     if (light_pos) CUDA_TRY(cudaMemcpyAsync(light_pos, d_lp.p, 12 * n, cudaMemcpyDeviceToHost, s->stream));
     if (outcome) CUDA_TRY(cudaMemcpyAsync(outcome, d_out.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return IPT_OK;
+}
+
+int ipt_preview_batch(ipt_scene* s, const float* origins, const float* directions, size_t n, float* value) {
+    if (!s || !origins || !directions || !value) return fail(IPT_ERR_INVALID, "null argument");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    DevBuf<float> d_o, d_d, d_v;
+    CUDA_TRY(d_o.alloc(3 * n)); CUDA_TRY(d_d.alloc(3 * n)); CUDA_TRY(d_v.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(d_o.p, origins, 12 * n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_d.p, directions, 12 * n, cudaMemcpyHostToDevice, s->stream));
+    unsigned blocks = (unsigned)((n + IPT_BLOCK - 1) / IPT_BLOCK);
+#define CALL(SP, MS) k_preview_batch<SP, MS><<<blocks, IPT_BLOCK, stack_smem(s), s->stream>>>(s->dev, d_o.p, d_d.p, n, d_v.p)
+    DISPATCH_SM(s, CALL);
+#undef CALL
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(value, d_v.p, 4 * n, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return IPT_OK;
 }

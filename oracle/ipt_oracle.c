@@ -752,6 +752,23 @@ int ipt_oracle_trace_batch(const ipt_scene_desc* desc, const float* o, const flo
     return 0;
 }
 
+/* ray_power_preview (src/main.cpp:55-92) */
+int ipt_oracle_preview_batch(const ipt_scene_desc* desc, const float* o, const float* d, size_t n, int use_bvh, float* value) {
+    oscene* s = oscene_prepare(desc);
+    for (size_t i = 0; i < n; ++i) {
+        v3 oo = A3(o + 3 * i), dd = A3(d + 3 * i);
+        osurf si = trace_geometry(s, oo, dd, use_bvh);
+        olhit li = lighting_trace(s, oo, dd, NULL);
+        float v;
+        if (li.hit && (!si.hit || vlength(vsub(si.position, oo)) > vlength(vsub(li.position, oo)))) v = 1.0f;
+        else if (!si.hit) v = 0.0f;
+        else v = vdot(si.normal, vneg(dd)) / vlength(dd);
+        value[i] = v;
+    }
+    oscene_free(s);
+    return 0;
+}
+
 int ipt_oracle_camera_rays(const ipt_scene_desc* desc, const float* xy, size_t n, float* o, float* d) {
     for (size_t i = 0; i < n; ++i) {
         v3 oo, dd;

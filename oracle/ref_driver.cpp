@@ -347,6 +347,13 @@ void iptref_arealight(const float* origin, const float* xa, const float* ya, flo
     *surface_power = li ? li->surface_power : 0.0f;
 }
 
+// ray_power_preview (src/main.cpp:55-92), the reference's alternative estimator, for n rays
+void iptref_preview_batch(int scene, size_t n, const float* o, const float* d, float* value) {
+    StatsNode stats;
+    for (size_t i = 0; i < n; ++i)
+        value[i] = ray_power_preview(*g_scenes[scene].geometry, *g_scenes[scene].lighting, v3(o + 3 * i), v3(d + 3 * i), 0, 0, &stats);
+}
+
 float iptref_ray_power(int scene, const float* o, const float* d, int depth, int n) {
     StatsNode stats;
     return ray_power(*g_scenes[scene].geometry, *g_scenes[scene].lighting, v3(o), v3(d), depth, n, &stats);

@@ -7,7 +7,7 @@ the GPU box, the reference sources do not.
 Fixtures:
   kat_<scene>.npz    bit-exact known answers of the reference's own functions on a fixed ray batch:
                      Camera::sampleRay, Geometry::traceRay (hit, position, normal, curvature),
-                     Lighting::traceRayToLight (hit, position, power), camera fields, light fields.
+                     Lighting::traceRayToLight (hit, position, power), ray_power_preview, camera fields, light fields.
   ddf_kat.npz        Ddf::value known answers (src/libddf/test_ddf.cpp:181-223 and a direction sweep),
                      AreaLight KAT (src/lighting/test_lighting.cpp:130-144), GridRenderPlane::addRay KAT.
   image_<scene>.npz  sum / sumsq / count of the reference estimator (ray_power_recursive, n_rays=16, depth_max=4)
@@ -72,9 +72,10 @@ def make_kats():
         g = ref.trace_geometry(h, o, d)
         l = ref.trace_light(h, o, d)
         lights = np.stack([ref.light_fields(h, i) for i in range(ref.light_count(h))])
+        preview = ref.preview_batch(h, o, d)
         np.savez_compressed(HERE / f"kat_{scene.replace(':', '_')}.npz", xy=xy, cam_o=co, cam_d=cd, o=o, d=d, hit=g["hit"], pos=g["pos"],
                             normal=g["normal"], curvature=g["curvature"], lhit=l["hit"], lpos=l["pos"], lpower=l["power"],
-                            camera=ref.camera_fields(h), lights=lights)
+                            camera=ref.camera_fields(h), lights=lights, preview=preview)
         print(scene, "rays", len(o), "hits", int(g["hit"].sum()), "light hits", int(l["hit"].sum()))
 
 

@@ -92,6 +92,12 @@ class Oracle:
         assert rc == 0
         return dict(prim=prim, t=t, pos=pos, normal=normal, light=light, light_pos=lpos, outcome=outcome)
 
+    def preview_batch(self, desc_ptr, o, d, use_bvh=0):
+        o, d = _f32(o).reshape(-1, 3), _f32(d).reshape(-1, 3)
+        v = np.empty(o.shape[0], np.float32)
+        self.lib.ipt_oracle_preview_batch(desc_ptr, _p(o, f32p), _p(d, f32p), C.c_size_t(o.shape[0]), use_bvh, _p(v, f32p))
+        return v
+
     def camera_rays(self, desc_ptr, xy):
         xy = _f32(xy).reshape(-1, 2)
         n = xy.shape[0]
@@ -284,6 +290,12 @@ class Ref:
         self.lib.iptref_arealight(_p(a[0], f32p), _p(a[1], f32p), _p(a[2], f32p), C.c_float(power), int(triangle),
                                   _p(a[3], f32p), _p(a[4], f32p), C.byref(area), C.byref(hit), C.byref(sp))
         return area.value, bool(hit.value), sp.value
+
+    def preview_batch(self, scene, o, d):
+        o, d = _f32(o).reshape(-1, 3), _f32(d).reshape(-1, 3)
+        v = np.empty(o.shape[0], np.float32)
+        self.lib.iptref_preview_batch(scene, C.c_size_t(o.shape[0]), _p(o, f32p), _p(d, f32p), _p(v, f32p))
+        return v
 
     def ray_power(self, scene, o, d, depth, n):
         o, d = _f32(o), _f32(d)

@@ -43,6 +43,8 @@ def test_reference_known_answers_bit_exact(scene, lib):
     lhit = r["light"] != capi.IPT_NO_HIT
     assert np.array_equal(lhit, g["lhit"])
     assert np.array_equal(bits(r["light_pos"][lhit]), bits(g["lpos"][lhit]))
+    # ray_power_preview of the reference (main.cpp:55-92) on the same rays
+    assert np.array_equal(bits(sc.preview_batch(g["o"], g["d"])), bits(g["preview"]))
     # primitive ids recovered from the reference's normal / curvature
     prims = [sd.desc.prims[i] for i in range(sd.desc.n_prims)]
     curv = np.array([prims[p].curvature for p in r["prim"][hit]], np.float32)

@@ -46,6 +46,8 @@ def test_oracle_camera_and_trace_bit_exact(scene, lib, oracle):
     lhit = r["light"] != capi.IPT_NO_HIT
     assert np.array_equal(lhit, g["lhit"])
     assert np.array_equal(bits(r["light_pos"][lhit]), bits(g["lpos"][lhit]))
+    # ray_power_preview (main.cpp:55-92): deterministic first-hit shading
+    assert np.array_equal(bits(oracle.preview_batch(sd.ptr, g["o"], g["d"])), bits(g["preview"]))
     # curvature is carried per primitive
     prims = [sd.desc.prims[i] for i in range(sd.desc.n_prims)]
     curv = np.array([prims[p].curvature for p in r["prim"][hit]], np.float32)
