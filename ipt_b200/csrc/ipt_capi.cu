@@ -19,6 +19,7 @@
 
 using namespace iptd;
 
+#define IPT_LIGHT_BVH_MIN 8 // light sets larger than this get an LBVH
 #define IPT_CNT_WORDS (3 * IPT_MAX_DEPTH + 2) // ray counts, hit counts, persistent-kernel fetch cursors
 
 // ---------------------------------------------------------------------------------------------------
@@ -67,6 +68,7 @@ struct ipt_scene {
     DevLight* d_lights = nullptr;
     DevMaterial* d_mats = nullptr;
     LbvhDevice bvh{};
+    LbvhDevice light_bvh{};
     bool smallpt = false, mesh = false;
     Workspace ws;
     uint32_t* d_cnt = nullptr;
@@ -462,6 +464,31 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
         dv.tri_id = s->bvh.sorted_ids;
         dv.nodes = s->bvh.nodes;
     }
+    // many area lights: LBVH over them (nearest-light and all-hits density queries instead of O(L) scans)
+    {
+        bool all_area = desc->n_lights > 0;
+        for (uint32_t i = 0; i < desc->n_lights; ++i) all_area = all_area && desc->lights[i].kind <= IPT_LIGHT_AREA_TRIANGLE;
+        if (all_area && desc->n_lights > IPT_LIGHT_BVH_MIN) {
+            std::vector<float> ltris(9 * (size_t)desc->n_lights), extra(3 * (size_t)desc->n_lights);
+            for (uint32_t i = 0; i < desc->n_lights; ++i) {
+                const ipt_light& l = desc->lights[i];
+                std::memcpy(&ltris[9 * (size_t)i], l.position, 12);
+                std::memcpy(&ltris[9 * (size_t)i + 3], l.x_axis, 12);
+                std::memcpy(&ltris[9 * (size_t)i + 6], l.y_axis, 12);
+                extra[3 * (size_t)i] = l.kind == IPT_LIGHT_AREA_TRIANGLE ? 1.0f : 0.0f;
+                extra[3 * (size_t)i + 1] = lights[i].area;
+                extra[3 * (size_t)i + 2] = lights[i].weight;
+            }
+            std::string err;
+            if (lbvh_build(ltris.data(), desc->n_lights, s->stream, s->light_bvh, err, extra.data()) != 0) {
+                delete s;
+                return fail(IPT_ERR_CUDA, "light LBVH build failed: " + err);
+            }
+            dv.light_nodes = s->light_bvh.nodes;
+            dv.light_recs = s->light_bvh.tri_records;
+            dv.n_light_bvh = desc->n_lights;
+        }
+    }
     CUDA_TRY(cudaMalloc((void**)&s->d_cnt, sizeof(uint32_t) * IPT_CNT_WORDS));
     CUDA_TRY(cudaMalloc((void**)&s->d_stats, sizeof(unsigned long long) * ST_COUNT));
 
@@ -494,6 +521,7 @@ int ipt_scene_destroy(ipt_scene* s) {
     if (s->host_plane) ipt_plane_destroy(s->host_plane);
     free_workspace(s->ws);
     lbvh_free(s->bvh);
+    lbvh_free(s->light_bvh);
     cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
     if (s->pinned) cudaFreeHost(s->pinned);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);

@@ -158,10 +158,77 @@ __device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f
         lpos = e.position;
     }
 }
+// conservative ray/box test for the light LBVH (see slab() in ipt_trace.cuh); limit = farthest useful entry distance
+__device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, float limit) {
+    float t0x = (a.v[base] - o.x) * inv.x, t1x = (a.v[base + 4] - o.x) * inv.x;
+    float t0y = (a.v[base + 1] - o.y) * inv.y, t1y = (a.v[base + 5] - o.y) * inv.y;
+    float t0z = (a.v[base + 2] - o.z) * inv.z, t1z = (a.v[base + 6] - o.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    return tn <= tf * 1.0000003f && tn <= limit;
+}
+
+// One stack traversal of the light LBVH serving both queries of CollectionLighting:
+//   NEAREST: traceRayToLight (CollectionLighting.cpp:23-34): nearest hit by length(pos - origin), earliest index on ties
+//   !NEAREST: the mixture density sum_i w_i * DdfFromLight_i::value(d) over ALL lights the ray hits (ddf.cpp:156-162)
+template <bool NEAREST>
+__device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos) {
+    float best_len = IPT_INF, pdf_sum = 0.0f;
+    which = IPT_NO_HIT;
+    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float dlen = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t node = S.n_light_bvh > 1 ? 0u : 0x80000000u; // a single light is a lone leaf
+    while (true) {
+        if (node & 0x80000000u) {
+            uint32_t pos = node & 0x7FFFFFFFu;
+            f8 r0 = ldg256(&S.light_recs[4 * (size_t)pos]);
+            f8 r1 = ldg256(&S.light_recs[4 * (size_t)pos + 2]);
+            f3 corner = mk3(r0.v[0], r0.v[1], r0.v[2]), n = mk3(r0.v[3], r0.v[4], r0.v[5]), rel;
+            float t = isect_parallelogram(corner, n, mk3(r0.v[6], r0.v[7], r1.v[0]), mk3(r1.v[1], r1.v[2], r1.v[3]), r1.v[5] != 0.0f, o, d, &rel);
+            if (t != IPT_INF) {
+                f3 hp = xadd3(corner, rel);
+                uint32_t orig = __float_as_uint(r1.v[4]);
+                if (NEAREST) {
+                    float len = xlength3(xsub3(hp, o));
+                    if (len < best_len || (len == best_len && orig < which)) { best_len = len; which = orig; lpos = hp; }
+                } else {
+                    f3 dp = mk3(hp.x - o.x, hp.y - o.y, hp.z - o.z);
+                    float decay = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
+                    float cosinus = -(n.x * dp.x + n.y * dp.y + n.z * dp.z) * rsqrtf(decay);
+                    if (cosinus >= 0.0f) pdf_sum += r1.v[7] * __fdividef(decay, cosinus * r1.v[6]);
+                }
+            }
+            node = IPT_NO_HIT;
+        } else {
+            f8 n0 = ldg256(&S.light_nodes[node]);
+            f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[node]) + 32);
+            // entry distances are in units of t; a hit at length L has t = L / |d|
+            float limit = NEAREST ? (best_len / dlen) * 1.0001f + 1e-6f : IPT_INF;
+            bool h0 = light_box(n0, 0, o, inv, limit), h1 = light_box(n1, 0, o, inv, limit);
+            uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
+            node = IPT_NO_HIT;
+            if (h0 && h1) { node = left; stack[sp++] = right; }
+            else if (h0) node = left;
+            else if (h1) node = right;
+        }
+        if (node == IPT_NO_HIT) {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return NEAREST ? best_len : pdf_sum;
+}
+
 // nearest light, scanning in list order with strict `>` (CollectionLighting.cpp:23-34)
 __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos) {
     bool any = false;
     float best_len = 0.0f;
+    if (S.n_light_bvh) {
+        light_bvh_query<true>(S, o, d, which, lpos);
+        return which != IPT_NO_HIT;
+    }
     if (S.light_inline) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands

@@ -24,7 +24,8 @@ __device__ __forceinline__ uint32_t f2ord(float f) { uint32_t b = __float_as_uin
 __device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
 
 // per triangle: tight box of (v0, v0+e1, v0+e2); scene bounds of the box centres
-__global__ void k_lbvh_bounds(const float* __restrict__ tris, uint32_t n, float4* lo, float4* hi, uint32_t* cbounds /*[6] ord: min xyz, max xyz*/) {
+__global__ void k_lbvh_bounds(const float* __restrict__ tris, uint32_t n, float4* lo, float4* hi, uint32_t* cbounds /*[6] ord: min xyz, max xyz*/,
+                              const float* __restrict__ extra /* per primitive (kind, area, weight) or null; kind 0 = parallelogram */) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0, 0, 0};
     if (i < n) {
@@ -34,6 +35,11 @@ __global__ void k_lbvh_bounds(const float* __restrict__ tris, uint32_t n, float4
             float v0 = t[a], v1 = xadd(t[a], t[3 + a]), v2 = xadd(t[a], t[6 + a]);
             l[a] = fminf(v0, fminf(v1, v2));
             h[a] = fmaxf(v0, fmaxf(v1, v2));
+            if (extra && extra[3 * (size_t)i] == 0.0f) { // parallelogram ("diamond" area light): the fourth corner
+                float v3 = xadd(v1, t[6 + a]);
+                l[a] = fminf(l[a], v3);
+                h[a] = fmaxf(h[a], v3);
+            }
             float c = xmul(xadd(l[a], h[a]), 0.5f);
             mn[a] = mx[a] = f2ord(c);
         }
@@ -243,7 +249,7 @@ __global__ void k_lbvh_refit(const float4* __restrict__ tlo, const float4* __res
 }
 
 // per sorted position: the constants AreaLight's constructor derives (lighting.cpp:79-90) for the triangle
-__global__ void k_lbvh_records(const float* __restrict__ tris, const uint32_t* __restrict__ ids, uint32_t n, float4* rec) {
+__global__ void k_lbvh_records(const float* __restrict__ tris, const uint32_t* __restrict__ ids, uint32_t n, float4* rec, const float* __restrict__ extra) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float* t = tris + 9 * (size_t)ids[k];
@@ -265,7 +271,9 @@ __global__ void k_lbvh_records(const float* __restrict__ tris, const uint32_t* _
     rec[4 * (size_t)k] = make_float4(v0.x, v0.y, v0.z, nn.x);
     rec[4 * (size_t)k + 1] = make_float4(nn.y, nn.z, i00, i10);
     rec[4 * (size_t)k + 2] = make_float4(i20, i01, i11, i21);
-    rec[4 * (size_t)k + 3] = make_float4(__uint_as_float(ids[k]), 0.0f, 0.0f, 0.0f); // original index rides in the 64-byte record
+    // the original index rides in the 64-byte record; light sets add (kind, area, mixture weight)
+    const float* ex = extra ? extra + 3 * (size_t)ids[k] : nullptr;
+    rec[4 * (size_t)k + 3] = make_float4(__uint_as_float(ids[k]), ex ? ex[0] : 1.0f, ex ? ex[1] : 0.0f, ex ? ex[2] : 0.0f);
 }
 
 static inline void lbvh_free(LbvhDevice& b) {
@@ -274,13 +282,14 @@ static inline void lbvh_free(LbvhDevice& b) {
 }
 
 // Builds the LBVH for n triangles given in HOST memory (9 floats each). Returns 0 on success.
-static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st, LbvhDevice& out, std::string& err) {
+static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st, LbvhDevice& out, std::string& err, const float* host_extra = nullptr) {
 #define LB_TRY(expr)                                                     \
     do {                                                                 \
         cudaError_t e__ = (expr);                                        \
         if (e__ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e__); goto fail; } \
     } while (0)
     float* d_tris = nullptr;
+    float* d_extra = nullptr;
     float4 *d_lo = nullptr, *d_hi = nullptr;
     uint32_t *d_cb = nullptr, *d_ids2 = nullptr, *d_counters = nullptr, *d_leaf_parent = nullptr, *d_flags = nullptr;
     unsigned long long* d_keys2 = nullptr;
@@ -291,6 +300,10 @@ static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st
     {
         LB_TRY(cudaMalloc((void**)&d_tris, sizeof(float) * 9 * (size_t)n));
         LB_TRY(cudaMemcpyAsync(d_tris, host_tris, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice, st));
+        if (host_extra) {
+            LB_TRY(cudaMalloc((void**)&d_extra, sizeof(float) * 3 * (size_t)n));
+            LB_TRY(cudaMemcpyAsync(d_extra, host_extra, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+        }
         LB_TRY(cudaMalloc((void**)&d_lo, 16 * (size_t)n));
         LB_TRY(cudaMalloc((void**)&d_hi, 16 * (size_t)n));
         LB_TRY(cudaMalloc((void**)&d_cb, 24));
@@ -301,7 +314,7 @@ static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st
         LB_TRY(cudaMalloc((void**)&d_keys2, 8 * (size_t)n));
         LB_TRY(cudaMalloc((void**)&d_ids2, 4 * (size_t)n));
         LB_TRY(cudaMalloc((void**)&d_counters, 4 * (size_t)256 * nb));
-        k_lbvh_bounds<<<blocks, 256, 0, st>>>(d_tris, n, d_lo, d_hi, d_cb);
+        k_lbvh_bounds<<<blocks, 256, 0, st>>>(d_tris, n, d_lo, d_hi, d_cb, d_extra);
         k_lbvh_morton<<<blocks, 256, 0, st>>>(d_lo, d_hi, n, d_cb, out.sorted_keys, out.sorted_ids);
         unsigned long long *ka = out.sorted_keys, *kb = d_keys2;
         uint32_t *va = out.sorted_ids, *vb = d_ids2;
@@ -315,7 +328,7 @@ static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st
         }
         LB_TRY(cudaGetLastError());
         LB_TRY(cudaMalloc((void**)&out.tri_records, 64 * (size_t)n));
-        k_lbvh_records<<<blocks, 256, 0, st>>>(d_tris, out.sorted_ids, n, out.tri_records);
+        k_lbvh_records<<<blocks, 256, 0, st>>>(d_tris, out.sorted_ids, n, out.tri_records, d_extra);
         if (n > 1) {
             LB_TRY(cudaMalloc((void**)&out.nodes, sizeof(BvhNode) * (size_t)(n - 1)));
             LB_TRY(cudaMemsetAsync(out.nodes, 0, sizeof(BvhNode) * (size_t)(n - 1), st));
@@ -328,11 +341,11 @@ static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st
         LB_TRY(cudaGetLastError());
         LB_TRY(cudaStreamSynchronize(st));
     }
-    cudaFree(d_tris); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_cb); cudaFree(d_keys2); cudaFree(d_ids2);
+    cudaFree(d_extra); cudaFree(d_tris); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_cb); cudaFree(d_keys2); cudaFree(d_ids2);
     cudaFree(d_counters); cudaFree(d_leaf_parent); cudaFree(d_flags);
     return 0;
 fail:
-    cudaFree(d_tris); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_cb); cudaFree(d_keys2); cudaFree(d_ids2);
+    cudaFree(d_extra); cudaFree(d_tris); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_cb); cudaFree(d_keys2); cudaFree(d_ids2);
     cudaFree(d_counters); cudaFree(d_leaf_parent); cudaFree(d_flags);
     lbvh_free(out);
     return 1;

@@ -170,6 +170,9 @@ __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float 
     return dir;
 }
 
+template <bool NEAREST>
+__device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos); // ipt_kernels.cuh
+
 // UnionDdf::value over [lights..., sdf] (src/libddf/ddf.cpp:156-162) with the weights of main.cpp:143
 __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3 pos, f3 w, float sdf_val) {
     float lp = 0.0f;
@@ -177,6 +180,10 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i)
             if (i < (int)S.n_lights) lp += S.lights[i].weight * light_pdf(S.lights[i], pos, w);
+    } else if (S.n_light_bvh) {
+        uint32_t which;
+        f3 lpos;
+        lp = light_bvh_query<false>(S, pos, w, which, lpos);
     } else {
         for (uint32_t i = 0; i < S.n_lights; ++i) {
             const DevLight& L = S.lights_g[i];

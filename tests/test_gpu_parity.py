@@ -205,3 +205,37 @@ def test_plane_add_rays_matches_gridrenderplane(scenes):
     assert np.allclose(pix, g["plane_pixels"], rtol=2e-6)  # sum/count vs the reference's float running mean
     assert mx == pytest.approx(float(g["plane_max"]), rel=1e-3) or mx <= float(g["plane_max"])  # running max >= final max
     pl.close()
+
+
+def test_many_lights_through_the_light_lbvh(lib, oracle):
+    """CollectionLighting with many emitters (BASELINE configs[4]): light sets > 8 go through an LBVH on the device;
+    the reference scans linearly. Nearest light id / position must stay bit-exact, the mixture density equal."""
+    name = "lightgrid:12x12"
+    sd = capi.SceneDescription(name)
+    sc = capi.Scene(sd)
+    rng = np.random.default_rng(4)
+    # rays from the floor / sphere region up towards the ceiling grid, plus generic rays
+    n = 30000
+    o = np.stack([rng.uniform(-0.95, 0.95, n), rng.uniform(-0.95, 0.95, n), rng.uniform(-0.99, 0.5, n)], 1).astype(np.float32)
+    tgt = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), np.full(n, 0.99)], 1).astype(np.float32)
+    # a third of the rays aims inside an emitter (they are 0.01 wide), some through two of them in a row
+    lights = np.array([list(sd.desc.lights[i].position) for i in range(sd.desc.n_lights)], np.float32)
+    pick = rng.integers(0, len(lights), n // 3)
+    tgt[: n // 3] = lights[pick] + np.stack([rng.uniform(0, 0.01, n // 3), rng.uniform(0, 0.01, n // 3), np.zeros(n // 3)], 1).astype(np.float32)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    g = sc.trace_batch(o, d)
+    c = oracle.trace_batch(sd.ptr, o, d)
+    assert (c["light"] != capi.IPT_NO_HIT).sum() > 2000
+    assert np.array_equal(g["light"], c["light"]) and np.array_equal(bits(g["light_pos"]), bits(c["light_pos"]))
+    assert np.array_equal(g["outcome"], c["outcome"]) and np.array_equal(g["prim"], c["prim"])
+    pos = np.array([0.1, -0.3, -1.0], np.float32)
+    w = d[:4000]
+    assert np.allclose(sc.light_ddf_value(pos, w), oracle.light_ddf_value(sd.ptr, pos, w), rtol=2e-4, atol=1e-6)
+    p = capi.default_params(width=48, height=48, pass_count=2, depth_max=2, schedule=[16, 8], flags=capi.FLAG_KEEP_ZERO_WEIGHT)
+    s, q, cnt, st = sc.render_host(p)
+    ref = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 0)
+    scale = max(ref["sum"].max(), 1e-12)
+    assert (np.abs(s - ref["sum"]) / scale > 1e-5).mean() < 4e-3
+    assert abs(s.sum() - ref["sum"].sum()) <= 1e-4 * ref["sum"].sum()
+    sc.close()
