@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(IPT_BLOCK) k_mix_sample(const __grid_constant_
     DevMaterial m = material < IPT_INLINE_MATS ? S.mats[material] : S.mats_g[material];
     Sdf sdf = make_sdf(m, normal, d);
     Basis bn = make_basis(normal);
+    Basis bl = make_basis(sdf.refl);
     uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 1u, 0xDDF1u, k0, k1);
-    f3 x = mix_sample(S, sdf, bn, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+    f3 x = mix_sample(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
     w[3 * i] = x.x; w[3 * i + 1] = x.y; w[3 * i + 2] = x.z;
     bool zero = x.x == 0.0f && x.y == 0.0f && x.z == 0.0f;
     float sv = zero ? 0.0f : sdf_value(sdf, x);
@@ -193,7 +194,7 @@ __global__ void k_light_ddf_sample(const __grid_constant__ DevScene S, f3 pos, u
     float us = u01(r.x) * (1.0f - S.sdf_weight);
     Sdf dummy{};
     Basis bn{};
-    f3 x = S.n_lights ? mix_sample(S, dummy, bn, pos, us, u01(r.y), u01(r.z), u01(r.w)) : mk3(0, 0, 0);
+    f3 x = S.n_lights ? mix_sample(S, dummy, bn, bn, pos, us, u01(r.y), u01(r.z), u01(r.w)) : mk3(0, 0, 0);
     if (S.n_lights && !(us < (S.light_inline ? S.lights[S.n_lights - 1].cdf : S.lights_g[S.n_lights - 1].cdf))) x = mk3(0, 0, 0);
     w[3 * i] = x.x; w[3 * i + 1] = x.y; w[3 * i + 2] = x.z;
 }

@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
         float thr = 0.0f;
         uint32_t tag = 0, node = 0, pixel = 0, pass = 0;
         Sdf sdf;
-        Basis bn;
+        Basis bn, bl;
         float albedo = 1.0f;
         if (active) {
             float4 a = C.hit_a[i];
@@ -477,6 +477,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
             if (m.ddf == IPT_DDF_GLOSSY) din = oct_decode(__uint_as_float(b.z), __uint_as_float(b.w)); // only the glossy lobe needs it
             sdf = make_sdf(m, normal, din);
             bn = make_basis(normal);
+            bl = m.ddf == IPT_DDF_GLOSSY ? make_basis(sdf.refl) : bn;
         }
         for (uint32_t c = 0; c < n_children; ++c) {
             bool emit = false;
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
-                w = mix_sample(S, sdf, bn, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                w = mix_sample(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
                     if (C.flags & 4u) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)

@@ -14,6 +14,18 @@ namespace iptd {
 
 #define IPT_PI_F 3.14159265358979323846f
 
+// SFU square root / reciprocal (sqrt.approx / rcp.approx, ~1 ulp): sampling code only, never the exact routines
+__device__ __forceinline__ float fsqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float frcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 struct Basis { // columns of RotateDdf::transformation; c2 == the axis rotated to
     f3 c0, c1, c2;
 };
@@ -23,12 +35,12 @@ __device__ __forceinline__ Basis make_basis(f3 to) {
     float c = to.z;
     float axx = -to.y, axy = to.x; // cross((0,0,1), to) = (-to.y, to.x, 0)
     float len2 = axx * axx + axy * axy;
-    float s = sqrtf(len2);
+    float s = fsqrt(len2);
     float ax, ay;
     if (s < 1e-6f) { ax = 1.0f; ay = 0.0f; } // ddf_detail.h:77-78 degenerate axis -> (1,0,0)
-    else { float inv = 1.0f / s; ax = axx * inv; ay = axy * inv; }
+    else { float inv = frcp(s); ax = axx * inv; ay = axy * inv; }
     // with the degenerate axis the angle is still acos(c): c = +-1, sin = sqrt(1-c*c)
-    float sn = sqrtf(fmaxf(0.0f, 1.0f - c * c));
+    float sn = fsqrt(fmaxf(0.0f, 1.0f - c * c));
     float tx = (1.0f - c) * ax, ty = (1.0f - c) * ay;
     Basis b;
     b.c0 = mk3(c + tx * ax, tx * ay, -sn * ay);
@@ -58,9 +70,9 @@ __device__ __forceinline__ f3 base_sample(int kind, float u1, float u2) {
     float zc;
     if (kind == 0) zc = u1 * 2.0f - 1.0f;
     else if (kind == 1) zc = u1;
-    else if (kind == 2) zc = sqrtf(u1);
+    else if (kind == 2) zc = fsqrt(u1);
     else zc = exp2f(__log2f(u1) * (1.0f / ((float)kind + 1.0f))); // u1^(1/(n+1)); u1 = 0 -> 0
-    float r = sqrtf(fmaxf(0.0f, 1.0f - zc * zc));
+    float r = fsqrt(fmaxf(0.0f, 1.0f - zc * zc));
     // phi = 2*pi*u2 = pi*a + pi with a in [-1,1): cos(phi) = -cos(pi*a), sin(phi) = -sin(pi*a); the SFU sine/cosine are
     // accurate to ~4e-7 absolute on [-pi, pi], far below the sampling noise
     float a = (2.0f * u2 - 1.0f) * IPT_PI_F;
@@ -102,11 +114,12 @@ __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
     return s.wd * base_value(2, cn) + s.ws * base_value(s.exponent, dot3(s.refl, w));
 }
 // zero vector == failed sample. ul is the lobe-selection draw (ROLE_LOBE in the oracle).
-__device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, float u1, float u2, float ul) {
+// bl: basis about the mirror direction (glossy hits only; built once per hit, not per child)
+__device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, const Basis& bl, float u1, float u2, float ul) {
     if (s.ddf == IPT_DDF_COSINE) return rotate(bn, base_sample(2, u1, u2));
     f3 w;
     if (ul < s.wd) w = rotate(bn, base_sample(2, u1, u2));
-    else w = rotate(make_basis(s.refl), base_sample(s.exponent, u1, u2));
+    else w = rotate(bl, base_sample(s.exponent, u1, u2));
     if (dot3(s.normal, w) < 0.0f) return mk3(0, 0, 0);
     return w;
 }
@@ -196,7 +209,7 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
 // UnionDdf::sample (src/libddf/ddf.cpp:138-154): scan the running float sum of weights with one draw `us`; the first
 // component whose running sum exceeds it is sampled. r >= total (float rounding; uninitialised result in the
 // reference) is a failed sample. Both candidate directions are formed by every lane (no light-vs-sdf divergence).
-__device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, f3 pos, float us, float u1, float u2, float ul) {
+__device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, const Basis& bl, f3 pos, float us, float u1, float u2, float ul) {
     f3 wl = mk3(0, 0, 0);
     float acc = 0.0f;
     bool from_light = false;
@@ -217,7 +230,7 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
         if (lo < S.n_lights) { from_light = true; wl = light_sample_dir(S.lights_g[lo], pos, u1, u2); }
         acc = S.lights_g[S.n_lights - 1].cdf;
     }
-    f3 ws = sdf_sample(sdf, bn, u1, u2, ul);
+    f3 ws = sdf_sample(sdf, bn, bl, u1, u2, ul);
     if (from_light) return wl;
     acc += S.sdf_weight;
     if (us < acc) return ws;
