@@ -32,7 +32,20 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-WORKLOAD = dict(scene="cornell", width=1024, height=1024, depth_max=4, schedule=[16, 8, 4, 2], spp_total=1024)
+# The bench line is BASELINE configs[1] ("c2"); the other configs are parity-test cases, selectable for the record.
+WORKLOADS = {
+    "c1": dict(config="configs[0]", scene="box", width=640, height=640, depth_max=4, schedule=[16, 8, 4, 2], spp_total=1024, passes_per_step=16,
+               text="default scene of src/sample_scenes.cpp (make_scene_box: open unit box + sphere + one square light)"),
+    "c2": dict(config="configs[1]", scene="cornell", width=1024, height=1024, depth_max=4, schedule=[16, 8, 4, 2], spp_total=1024, passes_per_step=8,
+               text="Cornell-box-style scene 'cornell' (5 box planes, Lambert sphere, glossy sphere, ceiling area light)"),
+    "c3": dict(config="configs[2]", scene="mesh:1000000", width=1920, height=1080, depth_max=8, schedule=[1] * 8, spp_total=256, passes_per_step=4,
+               text="procedural 1M-triangle random mesh inside the open box, max depth 8"),
+    "c4": dict(config="configs[3]", scene="mesh:10000000", width=3840, height=2160, depth_max=8, schedule=[1] * 8, spp_total=4096, passes_per_step=1,
+               text="10M-triangle synthetic mesh, sample-sharded across the GPUs"),
+    "c5": dict(config="configs[4]", scene="lightgrid:100x100", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], spp_total=16, passes_per_step=1,
+               tile=(768, 768, 512, 512), text="many-light CollectionLighting scene (10k emitters), 512x512 crop of the 2048x2048 frame per step"),
+}
+WORKLOAD = dict(WORKLOADS["c2"])
 CPU_SAMPLE = dict(width=128, height=128)  # the CPU legs render the same view/estimator at this frame size
 
 
@@ -172,8 +185,8 @@ def run_reference_arm(args):
 
 def workload_text():
     w = WORKLOAD
-    return (f"BASELINE configs[1]: Cornell-box-style scene '{w['scene']}' (5 box planes, Lambert sphere, glossy sphere, ceiling area light), "
-            f"{w['width']}x{w['height']}, {w['spp_total']} spp job, split schedule {'/'.join(map(str, w['schedule']))}, depth {w['depth_max']}")
+    return (f"BASELINE {w['config']}: {w['text']}, {w['width']}x{w['height']}, {w['spp_total']} spp job, "
+            f"split schedule {'/'.join(map(str, w['schedule']))}, depth {w['depth_max']}")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -248,9 +261,13 @@ def run_ours(args):
     total_steps = args.warmup + args.steps
     first_pass = rank * total_steps * pps  # disjoint pass ranges per rank
 
+    tile = w.get("tile")
+    paths_per_pass = (tile[2] * tile[3]) if tile else W * H
+
     def params(step, flags=capi.FLAG_TIME_KERNELS):
+        kw = dict(tile_x0=tile[0], tile_y0=tile[1], tile_w=tile[2], tile_h=tile[3]) if tile else {}
         return capi.default_params(width=W, height=H, depth_max=w["depth_max"], schedule=w["schedule"], seed=args.seed,
-                                   pass_begin=first_pass + step * pps, pass_count=pps, flags=flags, batch_paths=args.batch_paths)
+                                   pass_begin=first_pass + step * pps, pass_count=pps, flags=flags, batch_paths=args.batch_paths, **kw)
 
     def sync():
         torch.cuda.synchronize()
@@ -265,7 +282,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     agg = dict(paths=0, rays=0, launches=0, ms_dev=0.0, ms_ext=0.0, ms_shade=0.0, ms_gen=0.0, ms_acc=0.0, n_ext=0, n_shade=0, queued=0,
-               surface=0, light=0, queue_bytes=0)
+               surface=0, light=0, queue_bytes=0, nodes=0, tris=0)
     sync()
     t0 = time.perf_counter()
     for s in range(args.steps):
@@ -273,7 +290,7 @@ def run_ours(args):
         agg["paths"] += st.paths; agg["rays"] += st.rays; agg["launches"] += st.kernel_launches; agg["ms_dev"] += st.ms_total
         agg["ms_ext"] += st.ms_extend; agg["ms_shade"] += st.ms_shade; agg["ms_gen"] += st.ms_generate; agg["ms_acc"] += st.ms_accumulate
         agg["n_ext"] += st.n_extend; agg["n_shade"] += st.n_shade; agg["surface"] += st.surface_hits; agg["light"] += st.light_hits
-        agg["queue_bytes"] += st.queue_bytes
+        agg["queue_bytes"] += st.queue_bytes; agg["nodes"] += st.bvh_nodes_visited; agg["tris"] += st.triangles_tested
     if world > 1:  # the only collective of the path: reduce the accumulators over NVLink
         dist.all_reduce(acc_sum); dist.all_reduce(acc_sq); dist.all_reduce(acc_cnt)
     sync()
@@ -321,7 +338,7 @@ def run_ours(args):
         # dominant kernel and its algorithmic bytes: ray records are 36 B, hit records 32 B
         children = agg["rays"] - agg["paths"]
         queued = (agg["queue_bytes"] - 72 * agg["rays"] - 8 * agg["paths"]) // 64
-        bytes_ext = 36 * agg["rays"] + 32 * queued + 8 * agg["light"]
+        bytes_ext = 36 * agg["rays"] + 32 * queued + 8 * agg["light"] + 64 * (agg["nodes"] + agg["tris"])  # + BVH nodes / triangle records
         bytes_shade = 32 * queued + 36 * children
         dom = "shade" if agg["ms_shade"] >= agg["ms_ext"] else "extend"
         dom_ms = agg["ms_shade"] if dom == "shade" else agg["ms_ext"]
@@ -339,7 +356,7 @@ def run_ours(args):
             "metric": "path-tracing throughput", "value": paths_all / elapsed / 1e6, "unit": "Mpaths/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_text(), "passes_per_step": pps, "paths_per_step_per_gpu": W * H * pps,
+            "config": {"workload": workload_text(), "passes_per_step": pps, "paths_per_step_per_gpu": paths_per_pass * pps,
                        "parallelism": f"pass-sharded x{world}" if world > 1 else "single GPU",
                        "l2": "per-step ray/hit queue working set (>1 GB) exceeds the 126 MB L2; no flush needed",
                        "batch_paths": args.batch_paths or (1 << 19)},
@@ -350,14 +367,18 @@ def run_ours(args):
                     "d2h_bytes_per_step": 12 * W * H, "steps": e2e_steps,
                     "call": "ipt_scene_set_camera + ipt_render_host (host sum/sumsq/count buffers)"},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": ("k_extend_mesh" if dom == "extend" and w["scene"].startswith("mesh") else f"k_{dom}"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "launches": dom_n, "avg_launch_ms": dom_ms / max(dom_n, 1),
                          "algorithmic_bytes_per_launch": dom_bytes / max(dom_n, 1),
-                         "whole_pipeline": {"queue_bytes": agg["queue_bytes"], "achieved_gbs": agg["queue_bytes"] / (agg["ms_dev"] * 1e-3) / 1e9,
-                                            "frac": agg["queue_bytes"] / (agg["ms_dev"] * 1e-3) / 1e9 / peak},
+                         "whole_pipeline": {"bytes": agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"]),
+                                            "achieved_gbs": (agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"])) / (agg["ms_dev"] * 1e-3) / 1e9,
+                                            "frac": (agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"])) / (agg["ms_dev"] * 1e-3) / 1e9 / peak},
                          "kernel_ms": {"generate": agg["ms_gen"], "extend": agg["ms_ext"], "shade": agg["ms_shade"], "accumulate": agg["ms_acc"]}},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and w["scene"] not in ("box", "cornell"):
+            line["cpu_baseline"] = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "port",
+                                    "sample": "not run: the reference has no mesh / 10k-light scene; see the c1/c2 workloads"}
+        elif world == 1 and not args.no_cpu_baseline:
             pool = CpuPool()
             paths = rays = 0
             t0 = time.perf_counter()
@@ -382,13 +403,18 @@ def main():
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--passes-per-step", type=int, default=8)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE configs[1], the bench line")
+    ap.add_argument("--passes-per-step", type=int, default=0)
     ap.add_argument("--batch-paths", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS[args.workload])
+    if args.passes_per_step <= 0:
+        args.passes_per_step = WORKLOAD["passes_per_step"]
     if args.impl == "reference":
         if args.steps == 128:
             args.steps = 8  # each step is a bounded sample: keep the default run within minutes

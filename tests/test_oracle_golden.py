@@ -129,3 +129,11 @@ def z_scores(s1, q1, n1, s2, q2, n2):
     z = np.zeros_like(m1, dtype=np.float64)
     z[lit] = (m1[lit] - m2[lit]) / np.sqrt(v1[lit] + v2[lit])
     return z, lit
+
+
+def test_high_spp_goldens_are_consistent_with_the_low_spp_ones():
+    """Two independent runs of the reference (different seeds, frame sizes): image means agree."""
+    for scene in ["box", "cornell"]:
+        a = np.load(GOLD / f"image_{scene}.npz"); b = np.load(GOLD / f"image_{scene}_hi.npz")
+        ma = a["sum"].sum() / a["count"].sum(); mb = b["sum"].sum() / b["count"].sum()
+        assert abs(ma - mb) / mb < 0.01
