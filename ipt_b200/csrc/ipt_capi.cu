@@ -862,7 +862,9 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     while ((1ull << idx_bits) < max_ray_w) ++idx_bits;
     uint32_t slot_bits = 32 - idx_bits;
     uint64_t total_paths = (uint64_t)tw * th * p->pass_count;
-    uint64_t batch = p->batch_paths ? p->batch_paths : (1u << 19);
+    // default batch: as many paths as keep the widest tree level near 2^28 rays (2^19 paths at 16/8/4/2; up to 2^23
+    // for narrow schedules such as depth 8 with one child per hit, whose deeper levels would otherwise be tiny launches)
+    uint64_t batch = p->batch_paths ? p->batch_paths : std::min<uint64_t>(1ull << 23, std::max<uint64_t>(1ull << 16, (1ull << 28) / max_ray_w));
     batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
     const uint64_t budget = 24ull << 30; // bytes of queue memory
     while (batch > 1024 && batch * (max_ray_w * 36 + max_hit_w * 32) > budget) batch >>= 1;
