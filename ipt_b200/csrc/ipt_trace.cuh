@@ -186,8 +186,11 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 #define IPT_LEAF_BATCH 10   // run the postponed triangle tests once this many lanes hold one
 #endif
 
+#ifndef IPT_MESH_MIN_BLOCKS
+#define IPT_MESH_MIN_BLOCKS 4
+#endif
 template <bool LAST>
-__global__ void __launch_bounds__(IPT_BLOCK, 3) k_extend_mesh(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+__global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth];
     uint32_t* next = &C.fetch[depth];
     const uint32_t lane = threadIdx.x & 31;

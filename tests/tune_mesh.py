@@ -2,9 +2,7 @@ import json, os, subprocess, sys
 sys.path.insert(0, '.')
 from ipt_b200 import build
 variants = {
-    "lb1": ["IPT_LEAF_BATCH=1"], "lb4": ["IPT_LEAF_BATCH=4"], "lb10": [], "lb16": ["IPT_LEAF_BATCH=16"], "lb24": ["IPT_LEAF_BATCH=24"],
-    "lb4_s12": ["IPT_LEAF_BATCH=4", "IPT_STACK_SHORT=12"], "lb1_s12_st4": ["IPT_LEAF_BATCH=1", "IPT_STACK_SHORT=12", "IPT_TRAV_STEPS=4"],
-    "lb10_st12": ["IPT_TRAV_STEPS=12"], "lb16_st16": ["IPT_LEAF_BATCH=16", "IPT_TRAV_STEPS=16"], "lb10_rf4": ["IPT_REFILL_MIN=4"], "lb10_rf16": ["IPT_REFILL_MIN=16"],
+    "mb4": [], "mb5": ["IPT_MESH_MIN_BLOCKS=5"], "mb6": ["IPT_MESH_MIN_BLOCKS=6"], "mb5_st24": ["IPT_MESH_MIN_BLOCKS=5", "IPT_TRAV_STEPS=24"],
 }
 sel = sys.argv[1].split(",") if len(sys.argv) > 1 else list(variants)
 for name in sel:
