@@ -157,6 +157,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # each step is a bounded sample (one pass of the CPU_SAMPLE frame per host core); shrink the frame for long runs so
+    # that `--steps K --warmup W` still ends within a few minutes (the rate does not depend on the frame size)
+    total = args.steps + args.warmup
+    side = 128 if total <= 20 else (96 if total <= 48 else 64)
+    CPU_SAMPLE.update(width=side, height=side)
     pool = CpuPool()
     for _ in range(args.warmup):
         pool.step()

@@ -239,3 +239,46 @@ def test_many_lights_through_the_light_lbvh(lib, oracle):
     assert (np.abs(s - ref["sum"]) / scale > 1e-5).mean() < 4e-3
     assert abs(s.sum() - ref["sum"].sum()) <= 1e-4 * ref["sum"].sum()
     sc.close()
+
+
+def test_edge_cases_and_argument_validation(scenes, oracle):
+    """Empty and ragged inputs, extreme parameters, and the error codes of the C ABI."""
+    sd, sc = scenes("box")
+    # empty batches
+    assert sc.trace_batch(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))["prim"].shape == (0,)
+    assert sc.preview_batch(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)).shape == (0,)
+    # zero passes: nothing accumulated, no error
+    s, q, c, st = sc.render_host(capi.default_params(width=16, height=16, pass_count=0))
+    assert st.paths == 0 and c.sum() == 0
+    # ragged frame, 1x1 tile in the last row/column, batch of one path
+    p = capi.default_params(width=37, height=23, pass_count=3, plane_mode=capi.PLANE_LINEAR, tile_x0=36, tile_y0=22, tile_w=1, tile_h=1, batch_paths=1)
+    s, q, c, st = sc.render_host(p)
+    assert st.paths == 3 and c[22, 36] == 3 and c.sum() == 3
+    o = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 0)
+    assert np.array_equal(c.astype(np.uint64), o["counters"])
+    # the deepest tree the ABI allows, one child per hit
+    p = capi.default_params(width=24, height=24, pass_count=2, depth_max=16, schedule=[1] * 16)
+    s, q, c, st = sc.render_host(p)
+    assert st.rays_at_depth[15] <= st.rays_at_depth[1] and np.isfinite(s).all()
+    # GUI plane mapping (Gui::addRay, gui.cpp:168-172): yi = H - y*H, clamped: unlike GridRenderPlane every row is hit once per pass
+    s, q, c, st = sc.render_host(capi.default_params(width=20, height=20, pass_count=2, plane_mode=capi.PLANE_GUI))
+    assert c.sum() == 800 and (c == 2).all()
+    # errors: every one is reported through the status code + ipt_last_error, nothing falls back
+    for bad in [dict(depth_max=0), dict(depth_max=17), dict(width=16, height=16, tile_x0=10, tile_w=10, tile_h=4), dict(plane_mode=7),
+                dict(depth_max=4, schedule=[60000, 60000, 60000, 2])]:
+        with pytest.raises(capi.IptError) as e:
+            sc.render_host(capi.default_params(**{**dict(width=16, height=16), **bad}))
+        assert e.value.code in (1, 4), bad
+    pl = capi.Plane(sc, 8, 8)
+    with pytest.raises(capi.IptError):
+        pl.render(capi.default_params(width=16, height=16))  # plane / frame size mismatch
+    pl.close()
+    # scene descriptions are validated: a box plane must be an axis-aligned unit vector
+    sd2 = capi.SceneDescription("box")
+    sd2.desc.prims[0].p[1] = 0.5
+    with pytest.raises(capi.IptError):
+        capi.Scene(sd2)
+    sd2.desc.prims[0].p[1] = 0.0
+    sd2.desc.prims[5].material = 9
+    with pytest.raises(capi.IptError):
+        capi.Scene(sd2)
