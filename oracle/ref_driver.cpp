@@ -354,6 +354,16 @@ void iptref_preview_batch(int scene, size_t n, const float* o, const float* d, f
         value[i] = ray_power_preview(*g_scenes[scene].geometry, *g_scenes[scene].lighting, v3(o + 3 * i), v3(d + 3 * i), 0, 0, &stats);
 }
 
+// The reference's own estimator (ray_power_recursive, src/main.cpp:98-184) run on Geometry / Lighting objects that were
+// created OUTSIDE this library (e.g. ipt_b200's host classes): the drop-in check of oracle/ab_dropin.cpp.
+float iptref_ray_power_on(const void* geometry, const void* lighting, const float* o, const float* d, int depth, int n) {
+    StatsNode stats;
+    return ray_power(*static_cast<const Geometry*>(geometry), *static_cast<const Lighting*>(lighting), v3(o), v3(d), depth, n, &stats);
+}
+// ... and the reference's own objects handed out, so that the same rays can be run on both.
+const void* iptref_scene_geometry(int scene) { return g_scenes[scene].geometry.get(); }
+const void* iptref_scene_lighting(int scene) { return g_scenes[scene].lighting.get(); }
+
 float iptref_ray_power(int scene, const float* o, const float* d, int depth, int n) {
     StatsNode stats;
     return ray_power(*g_scenes[scene].geometry, *g_scenes[scene].lighting, v3(o), v3(d), depth, n, &stats);

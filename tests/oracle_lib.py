@@ -48,6 +48,19 @@ def build_ref():
     return REF_SO if REF_SO.exists() else None
 
 
+DROPIN = ROOT / "oracle" / "_ref" / "ab_dropin"
+
+
+def build_dropin():
+    """oracle/_ref/ab_dropin (ipt_b200's host classes compiled against the reference's headers + the reference's own
+    estimator): built where the reference sources exist, else the prebuilt binary if it travelled with the snapshot."""
+    if REF_SRC.exists() and (ROOT / "ipt_b200" / "lib" / "libipt_b200.so").exists():
+        deps = [ROOT / "oracle" / "ab_dropin.cpp", ROOT / "ipt_b200" / "host" / "device_plugins.cpp", ROOT / "ipt_b200" / "host" / "device_plugins.hpp", REF_SO]
+        if _stale(DROPIN, deps):
+            subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref", "dropin", f"REF={REF_SRC}"], check=True, capture_output=True)
+    return DROPIN if DROPIN.exists() else None
+
+
 def _p(a, t):
     return a.ctypes.data_as(t) if a is not None else None
 

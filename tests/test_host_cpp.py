@@ -60,3 +60,32 @@ def test_render_sample_through_the_cpp_interfaces(scene, host_demo, oracle):
     assert out["light_hit"] in (0, 1)
     lv = oracle.light_ddf_value(sd.ptr, [0.2, -0.8, -1.0], [[0, 0, 1]])[0]
     assert abs(out["light_ddf_value"] - lv) <= 1e-4 * max(lv, 1e-6)
+
+
+def test_dropin_binary_builds_against_reference_headers(lib):
+    import oracle_lib
+
+    if not oracle_lib.REF_SRC.exists():
+        pytest.skip("no reference sources here")
+    exe = oracle_lib.build_dropin()
+    assert exe is not None and exe.exists()
+
+
+@pytest.mark.gpu
+def test_reference_estimator_runs_on_ipt_b200_objects(lib):
+    """oracle/ab_dropin.cpp: the reference's compiled ray_power_recursive calls Geometry::traceRay /
+    Lighting::traceRayToLight / distributionInPoint / Ddf::sample / Ddf::value on ipt_b200's host objects (every call
+    evaluated on the GPU): single-ray results equal the reference's own objects to the bit, the estimate agrees
+    statistically."""
+    import oracle_lib
+
+    exe = oracle_lib.build_dropin()
+    if exe is None:
+        pytest.skip("oracle/_ref/ab_dropin not available (built where /root/reference exists)")
+    r = subprocess.run([str(exe), "box", "1500"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["geometry_equal"] == out["rays"] and out["geometry_hits"] > 0.5 * out["rays"]
+    assert out["light_equal"] == out["rays"] and out["light_hits"] > 50
+    assert abs(out["mean_reference_objects"] - out["mean_ipt_b200_objects"]) < 4 * out["standard_error"] + 1e-4
+    assert out["mean_reference_objects"] > 0
