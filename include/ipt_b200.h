@@ -239,6 +239,11 @@ int ipt_plane_destroy(ipt_plane* plane);
 int ipt_plane_download(ipt_plane* plane, float* sum, float* sumsq, uint32_t* count);     /* device -> host */
 int ipt_plane_upload(ipt_plane* plane, const float* sum, const float* sumsq, const uint32_t* count); /* resume */
 int ipt_plane_device_ptrs(ipt_plane* plane, float** d_sum, float** d_sumsq, uint32_t** d_count);
+/* The path's ONLY collective: element-wise sum of sum / sumsq / count over all ranks of an NCCL communicator (one
+ * process or thread per GPU, each rendering its own pass range; replaces the mutex-guarded running mean that merges the
+ * reference's four threads, src/gui.cpp:165-182). `nccl_comm` is an ncclComm_t owned by the host application. The
+ * library links against no NCCL: it resolves ncclAllReduce from the NCCL already loaded in the process (libnccl.so.2). */
+int ipt_plane_allreduce(ipt_plane* plane, void* nccl_comm);
 /* GridRenderPlane state after the same samples: pixels = sum/count, pixel_counters, max_value (GridRenderPlane.h:9-12). */
 int ipt_plane_resolve(ipt_plane* plane, float* pixels, uint64_t* pixel_counters, float* max_value);
 

@@ -27,6 +27,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-Xcompiler", "-fPIC,-ffp-contract=off",
     "-shared",
+    "-ldl",
 ]
 
 

@@ -113,6 +113,7 @@ SIGNATURES = {
     "ipt_plane_download": (C.c_int, [_vp, f32p, f32p, u32p]),
     "ipt_plane_upload": (C.c_int, [_vp, f32p, f32p, u32p]),
     "ipt_plane_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "ipt_plane_allreduce": (C.c_int, [_vp, _vp]),
     "ipt_plane_resolve": (C.c_int, [_vp, f32p, u64p, f32p]),
     "ipt_render": (C.c_int, [_vp, _vp, C.POINTER(RenderParams), C.POINTER(RenderStats)]),
     "ipt_render_host": (C.c_int, [_vp, C.POINTER(RenderParams), f32p, f32p, u32p, C.POINTER(RenderStats)]),
@@ -328,6 +329,10 @@ class Plane:
         s, q = _f32(s).ravel(), _f32(q).ravel()
         c = np.ascontiguousarray(c, np.uint32).ravel()
         check(load().ipt_plane_upload(self.handle, _ptr(s, f32p), _ptr(q, f32p), _ptr(c, u32p)))
+
+    def allreduce(self, nccl_comm):
+        """ipt_plane_allreduce with an ncclComm_t (integer / c_void_p) of the calling process."""
+        check(load().ipt_plane_allreduce(self.handle, nccl_comm))
 
     def resolve(self):
         n = self.width * self.height

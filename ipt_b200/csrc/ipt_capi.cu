@@ -9,6 +9,8 @@
 #include "ipt_lbvh.cuh"
 #include "ipt_trace.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -778,6 +780,33 @@ int ipt_plane_device_ptrs(ipt_plane* p, float** d_sum, float** d_sumsq, uint32_t
     if (d_sum) *d_sum = p->sum;
     if (d_sumsq) *d_sumsq = p->sumsq;
     if (d_count) *d_count = p->count;
+    return IPT_OK;
+}
+int ipt_plane_allreduce(ipt_plane* p, void* nccl_comm) {
+    if (!p || !nccl_comm) return fail(IPT_ERR_INVALID, "null argument");
+    // ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+    typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    typedef const char* (*errstr_fn)(int);
+    static allreduce_fn all_reduce = nullptr;
+    static errstr_fn err_string = nullptr;
+    if (!all_reduce) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); // the copy the host application already uses
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+        if (!h) return fail(IPT_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+        all_reduce = (allreduce_fn)dlsym(h, "ncclAllReduce");
+        err_string = (errstr_fn)dlsym(h, "ncclGetErrorString");
+        if (!all_reduce) return fail(IPT_ERR_UNSUPPORTED, "ncclAllReduce not found in libnccl");
+    }
+    CUDA_TRY(cudaSetDevice(p->scene->device));
+    const size_t n = (size_t)p->width * p->height;
+    cudaStream_t st = p->scene->stream;
+    const int nccl_float32 = 7, nccl_uint32 = 3, nccl_sum = 0; // nccl.h: ncclFloat32, ncclUint32, ncclSum
+    int rc = all_reduce(p->sum, p->sum, n, nccl_float32, nccl_sum, nccl_comm, st);
+    if (!rc) rc = all_reduce(p->sumsq, p->sumsq, n, nccl_float32, nccl_sum, nccl_comm, st);
+    if (!rc) rc = all_reduce(p->count, p->count, n, nccl_uint32, nccl_sum, nccl_comm, st);
+    if (rc) return fail(IPT_ERR_CUDA, std::string("ncclAllReduce: ") + (err_string ? err_string(rc) : "error"));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return IPT_OK;
 }
 int ipt_plane_resolve(ipt_plane* p, float* pixels, uint64_t* pixel_counters, float* max_value) {
