@@ -174,7 +174,8 @@ int ipt_scene_destroy(ipt_scene* scene);
 int ipt_scene_set_camera(ipt_scene* scene, const ipt_camera* camera);
 
 /* The reference's five scenes + this repo's benchmark scenes as descriptions:
- * "box" (make_scene_box, the default), "fractal", "smallpt", "square", "corner", "cornell" (C2),
+ * "box" (make_scene_box, the default), "fractal", "smallpt", "square", "corner", "openspheres", "cornell" (C2),
+ * "mixedlights" (one of every Light class over the default geometry),
  * "lightgrid:<rows>x<cols>" (C5), "mesh:<n>" (C3/C4: `n` generated triangles inside the C1 box).
  * The returned description and its arrays are owned by the library until ipt_scene_desc_free. */
 int ipt_sample_scene(const char* name, ipt_scene_desc** out);

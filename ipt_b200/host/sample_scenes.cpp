@@ -234,6 +234,22 @@ void scene_cornell(SceneHolder& s) {
     s.desc.camera = look(mk(0.0f, -3.2f, 0.0f), normalize(mk(0.0f, 1.0f, 0.0f)));
 }
 
+// One of every Light class over the default geometry (lighting.h:16-73 through CollectionLighting.cpp:36-55):
+// same literals as iptref_scene_set_mixed_lights in oracle/ref_driver.cpp
+void scene_mixedlights(SceneHolder& s) {
+    scene_box(s);
+    s.lights.clear();
+    s.lights.push_back(square_light(mk(+0.1f, -0.8f - 0.1f, -0.15f), mk(0.0f, 0.0f, -1.0f), mk(0.0f, 0.2f, 0.0f), 1.0f));
+    s.lights.push_back(triangle_light(mk(-0.8f, -0.2f, 0.6f), mk(0.3f, 0.0f, 0.0f), mk(0.0f, 0.0f, -0.3f), 0.5f));
+    s.lights.push_back(sphere_light(mk(-0.7f, -0.5f, -0.8f), 0.1f, 0.7f));
+    ipt_light outer = sphere_light(mk(0, 0, 0), 10.0f, 20.0f); // addOuterLight: InvertedSphereLight at the origin
+    outer.kind = IPT_LIGHT_SPHERE_INVERTED;
+    s.lights.push_back(outer);
+    ipt_light point = sphere_light(mk(0.9f, 0.0f, -0.8f), 0.0f, 1.0f); // addPointLight (virtual_radius is unused)
+    point.kind = IPT_LIGHT_POINT;
+    s.lights.push_back(point);
+}
+
 // BASELINE.json configs[4] ("C5"): rows x cols square emitters under the ceiling over the C1 geometry
 void scene_lightgrid(SceneHolder& s, int rows, int cols) {
     scene_box(s);
@@ -304,6 +320,7 @@ int ipt_sample_scene(const char* name, ipt_scene_desc** out) {
     else if (n == "corner") scene_corner(*s);
     else if (n == "openspheres") scene_openspheres(*s);
     else if (n == "cornell") scene_cornell(*s);
+    else if (n == "mixedlights") scene_mixedlights(*s);
     else if (n.rfind("lightgrid:", 0) == 0) {
         int r = 0, c = 0;
         if (std::sscanf(n.c_str() + 10, "%dx%d", &r, &c) != 2 || r <= 0 || c <= 0) { delete s; return IPT_ERR_INVALID; }

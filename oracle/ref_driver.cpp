@@ -231,6 +231,19 @@ int iptref_scene_set_light_grid(int scene, int rows, int cols, float side, float
     return rows * cols;
 }
 
+// Replaces the scene's lights with one of every Light class (lighting.h:16-73) through CollectionLighting's own add*
+// calls; the same literals are in ipt_b200/host/sample_scenes.cpp ("mixedlights").
+int iptref_scene_set_mixed_lights(int scene) {
+    shared_ptr<CollectionLighting> lighting = make_shared<CollectionLighting>();
+    lighting->addSquareLight(vec3{+0.1f, -0.8f - 0.1f, -0.15f}, vec3(0.0f, 0.0f, -1.0f), vec3{0.0f, 0.2f, 0.0f}, 1.0f);
+    lighting->addTriangleLight(vec3(-0.8f, -0.2f, 0.6f), vec3(0.3f, 0.0f, 0.0f), vec3(0.0f, 0.0f, -0.3f), 0.5f);
+    lighting->addSphereLight(vec3(-0.7f, -0.5f, -0.8f), 0.1f, 0.7f);
+    lighting->addOuterLight(10.0f, 20.0f);
+    lighting->addPointLight(vec3(0.9f, 0.0f, -0.8f), 0.1f, 1.0f);
+    g_scenes[scene].lighting = lighting;
+    return 5;
+}
+
 void iptref_set_tree(int n, int dmax) { n_rays = n; depth_max = dmax; }
 void iptref_seed(long seed) { srand48(seed); }
 uint64_t iptref_rays_traced() { return g_rays_traced; }

@@ -4,11 +4,11 @@ from __future__ import annotations
 import numpy as np
 
 SCENES_REFERENCE = ["box", "fractal", "smallpt", "square", "corner", "openspheres"]
-SCENES_ANALYTIC = SCENES_REFERENCE + ["cornell"]
+SCENES_ANALYTIC = SCENES_REFERENCE + ["cornell", "mixedlights"]
 
 # (box centre, half extent) of the region secondary rays start from, per scene
 REGION = {
-    "box": ((0, 0, 0), 1.0), "cornell": ((0, 0, 0), 1.0), "corner": ((0, 0, 0), 1.0), "square": ((0, 0, -0.5), 1.0),
+    "box": ((0, 0, 0), 1.0), "mixedlights": ((0, 0, 0), 1.0), "cornell": ((0, 0, 0), 1.0), "corner": ((0, 0, 0), 1.0), "square": ((0, 0, -0.5), 1.0),
     "openspheres": ((0, 0, -0.6), 0.6), "fractal": ((0, 0, 0), 2.5), "smallpt": ((50, 40, 80), 45.0),
 }
 

@@ -205,6 +205,9 @@ class Ref:
                 r, c = name[10:].split("x")
                 h = self.lib.iptref_scene_create(b"box")
                 self.lib.iptref_scene_set_light_grid(h, int(r), int(c), C.c_float(0.01), C.c_float(0.99), C.c_float(1.0))
+            elif name == "mixedlights":
+                h = self.lib.iptref_scene_create(b"box")
+                self.lib.iptref_scene_set_mixed_lights(h)
             else:
                 h = self.lib.iptref_scene_create(name.encode())
             assert h >= 0, name

@@ -18,7 +18,8 @@ def _schedule(n, depth_max):
 
 
 @pytest.mark.parametrize("scene,n_rays,depth_max", [("box", 4, 3), ("cornell", 4, 3), ("corner", 4, 3), ("square", 8, 4),
-                                                    ("smallpt", 2, 3), ("fractal", 4, 4), ("openspheres", 4, 3), ("box", 3, 4)])
+                                                    ("smallpt", 2, 3), ("fractal", 4, 4), ("openspheres", 4, 3), ("box", 3, 4),
+                                                    ("mixedlights", 4, 3)])
 def test_whole_pass_bit_identical_to_reference(scene, n_rays, depth_max, lib, oracle, ref):
     """Verbatim src/main.cpp render_sample (640x640) vs the oracle, same srand48 seed: pixels, counters and ray count."""
     sd = capi.SceneDescription(scene)
@@ -44,7 +45,7 @@ def test_parametrised_loop_equals_verbatim_loop(ref):
     assert np.array_equal(bits(a["pixels"]), bits(b["pixels"])) and a["rays"] == b["rays"]
 
 
-@pytest.mark.parametrize("scene", ["box", "cornell", "lightgrid:3x3", "fractal"])
+@pytest.mark.parametrize("scene", ["box", "cornell", "lightgrid:3x3", "fractal", "mixedlights"])
 def test_mixture_samples_bit_identical(scene, lib, oracle, ref):
     """unite(light_ddf,1,sdf,1) at a surface hit (main.cpp:142-143): sample(), value() and sdf value() sequences."""
     sd = capi.SceneDescription(scene)
@@ -77,7 +78,7 @@ def test_light_ddf_value_and_sample(lib, oracle, ref):
     w = rng.normal(size=(300, 3)).astype(np.float32)
     w /= np.linalg.norm(w, axis=1, keepdims=True).astype(np.float32)
     w[:, 2] = np.abs(w[:, 2])
-    for scene in ["box", "lightgrid:3x3", "corner", "fractal"]:
+    for scene in ["box", "lightgrid:3x3", "corner", "fractal", "mixedlights"]:
         sd = capi.SceneDescription(scene)
         h = ref.scene(scene)
         pos = np.array([0.1, -0.5, -1.0], np.float32)
