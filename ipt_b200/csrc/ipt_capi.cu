@@ -62,6 +62,9 @@ struct Workspace {
 };
 
 struct ipt_scene {
+    // The reference calls render_sample from four threads on one Scene (main.cpp:258-277). One scene owns one stream and
+    // one workspace, so every entry point that touches them takes this lock: concurrent callers are serialised.
+    std::recursive_mutex mu;
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
@@ -536,6 +539,7 @@ int ipt_scene_destroy(ipt_scene* s) {
 
 int ipt_scene_set_camera(ipt_scene* s, const ipt_camera* camera) {
     if (!s || !camera) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     set_camera(s->dev, *camera);
     return IPT_OK;
 }
@@ -544,6 +548,7 @@ int ipt_scene_set_camera(ipt_scene* s, const ipt_camera* camera) {
 int ipt_trace_batch(ipt_scene* s, const float* origins, const float* directions, size_t n, uint32_t* prim_id, float* t,
                     uint32_t* light_id, float* light_pos, uint32_t* outcome) {
     if (!s || !origins || !directions) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_o, d_d, d_t, d_lp;
@@ -568,6 +573,7 @@ int ipt_trace_batch(ipt_scene* s, const float* origins, const float* directions,
 
 int ipt_preview_batch(ipt_scene* s, const float* origins, const float* directions, size_t n, float* value) {
     if (!s || !origins || !directions || !value) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_o, d_d, d_v;
@@ -586,6 +592,7 @@ int ipt_preview_batch(ipt_scene* s, const float* origins, const float* direction
 
 int ipt_camera_rays(ipt_scene* s, const float* xy, size_t n, float* origins, float* directions) {
     if (!s || !xy || !origins || !directions) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_xy, d_o, d_d;
@@ -601,6 +608,7 @@ int ipt_camera_rays(ipt_scene* s, const float* xy, size_t n, float* origins, flo
 
 int ipt_ddf_value(ipt_scene* s, int kind, const float* to, const float* dirs, size_t n, float* out) {
     if (!s || !dirs || !out || kind < 0) return fail(IPT_ERR_INVALID, "bad argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_w, d_out;
@@ -616,6 +624,7 @@ int ipt_ddf_value(ipt_scene* s, int kind, const float* to, const float* dirs, si
 
 int ipt_ddf_sample(ipt_scene* s, int kind, const float* to, uint64_t seed, size_t n, float* dirs) {
     if (!s || !dirs || kind < 0) return fail(IPT_ERR_INVALID, "bad argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_w;
@@ -631,6 +640,7 @@ int ipt_ddf_sample(ipt_scene* s, int kind, const float* to, uint64_t seed, size_
 int ipt_mix_sample(ipt_scene* s, const float origin[3], const float direction[3], uint64_t seed, size_t n, float* dirs,
                    float* mix_value_out, float* sdf_value_out) {
     if (!s || !origin || !direction || !dirs || !mix_value_out || !sdf_value_out) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_w, d_m, d_s;
@@ -654,6 +664,7 @@ int ipt_mix_sample(ipt_scene* s, const float origin[3], const float direction[3]
 
 int ipt_light_ddf_value(ipt_scene* s, const float pos[3], const float* dirs, size_t n, float* out) {
     if (!s || !pos || !dirs || !out) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_w, d_out;
@@ -668,6 +679,7 @@ int ipt_light_ddf_value(ipt_scene* s, const float pos[3], const float* dirs, siz
 
 int ipt_light_ddf_sample(ipt_scene* s, const float pos[3], uint64_t seed, size_t n, float* dirs) {
     if (!s || !pos || !dirs) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(s->device));
     DevBuf<float> d_w;
@@ -681,6 +693,7 @@ int ipt_light_ddf_sample(ipt_scene* s, const float pos[3], uint64_t seed, size_t
 
 int ipt_bvh_export(ipt_scene* s, ipt_bvh_node* nodes, uint32_t* sorted_prims, uint64_t* morton, uint64_t* n_nodes) {
     if (!s) return fail(IPT_ERR_INVALID, "null scene");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (!s->mesh) return fail(IPT_ERR_INVALID, "scene has no triangle mesh");
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -716,6 +729,7 @@ int ipt_plane_wrap(ipt_scene* s, uint32_t width, uint32_t height, float* d_sum, 
 }
 int ipt_plane_clear(ipt_plane* p) {
     if (!p) return fail(IPT_ERR_INVALID, "null plane");
+    std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     CUDA_TRY(cudaSetDevice(p->scene->device));
     size_t n = (size_t)p->width * p->height;
     CUDA_TRY(cudaMemsetAsync(p->sum, 0, 4 * n, p->scene->stream));
@@ -726,6 +740,7 @@ int ipt_plane_clear(ipt_plane* p) {
 }
 int ipt_plane_add_rays(ipt_plane* p, uint32_t plane_mode, size_t n, const float* x, const float* y, const float* value) {
     if (!p || !x || !y || !value || plane_mode > IPT_PLANE_LINEAR) return fail(IPT_ERR_INVALID, "bad argument");
+    std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     if (n == 0) return IPT_OK;
     CUDA_TRY(cudaSetDevice(p->scene->device));
     cudaStream_t st = p->scene->stream;
@@ -755,6 +770,7 @@ int ipt_plane_destroy(ipt_plane* p) {
 }
 int ipt_plane_download(ipt_plane* p, float* sum, float* sumsq, uint32_t* count) {
     if (!p) return fail(IPT_ERR_INVALID, "null plane");
+    std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     CUDA_TRY(cudaSetDevice(p->scene->device));
     size_t n = (size_t)p->width * p->height;
     cudaStream_t st = p->scene->stream;
@@ -766,6 +782,7 @@ int ipt_plane_download(ipt_plane* p, float* sum, float* sumsq, uint32_t* count) 
 }
 int ipt_plane_upload(ipt_plane* p, const float* sum, const float* sumsq, const uint32_t* count) {
     if (!p || !sum || !sumsq || !count) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     CUDA_TRY(cudaSetDevice(p->scene->device));
     size_t n = (size_t)p->width * p->height;
     cudaStream_t st = p->scene->stream;
@@ -784,6 +801,7 @@ int ipt_plane_device_ptrs(ipt_plane* p, float** d_sum, float** d_sumsq, uint32_t
 }
 int ipt_plane_allreduce(ipt_plane* p, void* nccl_comm) {
     if (!p || !nccl_comm) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     // ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
     typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
     typedef const char* (*errstr_fn)(int);
@@ -811,6 +829,7 @@ int ipt_plane_allreduce(ipt_plane* p, void* nccl_comm) {
 }
 int ipt_plane_resolve(ipt_plane* p, float* pixels, uint64_t* pixel_counters, float* max_value) {
     if (!p || !pixels) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     CUDA_TRY(cudaSetDevice(p->scene->device));
     size_t n = (size_t)p->width * p->height;
     DevBuf<float> d_pix;
@@ -862,6 +881,7 @@ static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t
 
 int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_render_stats* stats) {
     if (!s || !plane || !p) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (plane->scene != s) return fail(IPT_ERR_INVALID, "plane belongs to another scene");
     if (!p->width || !p->height || plane->width != p->width || plane->height != p->height)
         return fail(IPT_ERR_INVALID, "plane size does not match render params");
@@ -1026,6 +1046,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
 
 int ipt_render_host(ipt_scene* s, const ipt_render_params* p, float* sum, float* sumsq, uint32_t* count, ipt_render_stats* stats) {
     if (!s || !p || !sum) return fail(IPT_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (s->host_plane && (s->host_plane->width != p->width || s->host_plane->height != p->height)) {
         ipt_plane_destroy(s->host_plane);
         s->host_plane = nullptr;

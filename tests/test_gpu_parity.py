@@ -382,3 +382,25 @@ def test_many_spheres_take_the_generic_primitive_scan(lib, oracle):
     scale = max(ref["sum"].max(), 1e-12)
     assert (np.abs(s - ref["sum"]) / scale > 1e-5).mean() < 6e-3
     sc.close()
+
+
+def test_four_threads_on_one_scene_like_main_cpp(scenes):
+    """main.cpp:258-277 calls render_sample from four threads on one Scene. Concurrent callers of one ipt_scene are
+    serialised by the library; every thread must get exactly the result of a sequential call."""
+    import threading
+
+    sd, sc = scenes("cornell")
+    jobs = [capi.default_params(width=64, height=64, pass_begin=8 * k, pass_count=8, seed=3) for k in range(4)]
+    expect = [sc.render_host(p) for p in jobs]
+    got = [None] * 4
+
+    def work(k):
+        for _ in range(3):
+            got[k] = sc.render_host(jobs[k])
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for k in range(4):
+        assert np.array_equal(got[k][2], expect[k][2])
+        assert np.allclose(got[k][0], expect[k][0], rtol=1e-5, atol=1e-6)
