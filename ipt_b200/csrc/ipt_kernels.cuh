@@ -17,9 +17,6 @@
 // separates the stages.
 #pragma once
 #include "ipt_shading.cuh"
-#ifndef IPT_DEFER_APPEND
-#define IPT_DEFER_APPEND 0 // 1: consume the slot-reserving atomicAdd one iteration later; measured slower (spills), profiles/tuning_r01.md
-#endif
 #ifndef IPT_SHADE_MIN_BLOCKS
 #define IPT_SHADE_MIN_BLOCKS 2
 #endif
@@ -317,10 +314,6 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t n_surface = 0, n_light = 0, n_miss = 0, n_dropped = 0;
     TraceCounters tc{0, 0};
-    uint32_t pend_ballot = 0, pend_base = 0;
-    bool pend_emit = false;
-    float4 pend_a = make_float4(0, 0, 0, 0);
-    uint4 pend_b = make_uint4(0, 0, 0, 0);
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
         uint32_t i = base + lane;
         bool active = i < n;
@@ -353,46 +346,21 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
             }
         }
         if (!LAST) {
-            // warp-aggregated append with a DEFERRED write: the atomicAdd that reserves slots is issued now, its result
-            // is consumed one loop iteration later, so its L2 round trip overlaps the next 32 rays' intersection work
+            // warp-aggregated append: one atomicAdd per warp reserves the slots of all its emitting lanes
             uint32_t ballot = __ballot_sync(0xffffffffu, emit);
-            uint32_t basepos = 0;
-            if (ballot && lane == 0) basepos = atomicAdd(&C.cnt[2 * depth + 1], __popc(ballot));
-            if (pend_ballot) {
-                uint32_t b0 = __shfl_sync(0xffffffffu, pend_base, 0);
-                if (pend_emit) {
-                    uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
-                    C.hit_a[j] = pend_a;
-                    C.hit_b[j] = pend_b;
+            if (ballot) {
+                uint32_t basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&C.cnt[2 * depth + 1], (uint32_t)__popc(ballot));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (emit) {
+                    uint32_t j = basepos + __popc(ballot & ((1u << lane) - 1u));
+                    f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), oc.surf.t);
+                    uint32_t iprim = oc.surf.tri_pos != IPT_NO_HIT ? S.n_prims + oc.surf.tri_pos : oc.surf.prim;
+                    float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
+                    C.hit_a[j] = make_float4(p.x, p.y, p.z, ro.w);
+                    C.hit_b[j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
                 }
             }
-            pend_ballot = ballot; pend_base = basepos; pend_emit = emit;
-            if (emit) {
-                f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), oc.surf.t);
-                uint32_t iprim = oc.surf.tri_pos != IPT_NO_HIT ? S.n_prims + oc.surf.tri_pos : oc.surf.prim;
-                float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
-                pend_a = make_float4(p.x, p.y, p.z, ro.w);
-                pend_b = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
-            }
-#if !IPT_DEFER_APPEND
-            if (pend_ballot) {
-                uint32_t b0 = __shfl_sync(0xffffffffu, pend_base, 0);
-                if (pend_emit) {
-                    uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
-                    C.hit_a[j] = pend_a;
-                    C.hit_b[j] = pend_b;
-                }
-                pend_ballot = 0;
-            }
-#endif
-        }
-    }
-    if (!LAST && pend_ballot) {
-        uint32_t b0 = __shfl_sync(0xffffffffu, pend_base, 0);
-        if (pend_emit) {
-            uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
-            C.hit_a[j] = pend_a;
-            C.hit_b[j] = pend_b;
         }
     }
     flush_stat(C.stats, ST_SURFACE, n_surface);
@@ -441,10 +409,6 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
     const float inv_n = 1.0f / (float)n_children;
     uint32_t n_failed = 0, n_pruned = 0, n_dropped = 0;
     uint32_t* out_count = &C.cnt[2 * (depth + 1)];
-    uint32_t pend_ballot = 0, pend_base = 0;
-    bool pend_emit = false;
-    float4 pend_o = make_float4(0, 0, 0, 0), pend_d = make_float4(0, 0, 0, 0);
-    float pend_x = -1.0f;
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
         uint32_t i = base + lane;
         bool active = i < n;
@@ -513,47 +477,20 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
                     }
                 }
             }
-            // warp-aggregated append, write deferred by one child (see k_extend)
+            // warp-aggregated append (see k_extend)
             uint32_t ballot = __ballot_sync(0xffffffffu, emit);
-            uint32_t basepos = 0;
-            if (ballot && lane == 0) basepos = atomicAdd(out_count, __popc(ballot));
-            if (pend_ballot) {
-                uint32_t b0 = __shfl_sync(0xffffffffu, pend_base, 0);
-                if (pend_emit) {
-                    uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
-                    C.ray_o[j] = pend_o;
-                    C.ray_d[j] = pend_d;
-                    C.ray_x[j] = pend_x;
+            if (ballot) {
+                uint32_t basepos = 0;
+                if (lane == 0) basepos = atomicAdd(out_count, (uint32_t)__popc(ballot));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (emit) {
+                    uint32_t j = basepos + __popc(ballot & ((1u << lane) - 1u));
+                    uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
+                    C.ray_o[j] = make_float4(pos.x, pos.y, pos.z, wgt);
+                    C.ray_d[j] = make_float4(w.x, w.y, w.z, __uint_as_float(ctag));
+                    C.ray_x[j] = child_sv;
                 }
             }
-            pend_ballot = ballot; pend_base = basepos; pend_emit = emit;
-            if (emit) {
-                uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
-                pend_o = make_float4(pos.x, pos.y, pos.z, wgt);
-                pend_d = make_float4(w.x, w.y, w.z, __uint_as_float(ctag));
-                pend_x = child_sv;
-            }
-#if !IPT_DEFER_APPEND
-            if (pend_ballot) {
-                uint32_t b0 = __shfl_sync(0xffffffffu, pend_base, 0);
-                if (pend_emit) {
-                    uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
-                    C.ray_o[j] = pend_o;
-                    C.ray_d[j] = pend_d;
-                    C.ray_x[j] = pend_x;
-                }
-                pend_ballot = 0;
-            }
-#endif
-        }
-    }
-    if (pend_ballot) {
-        uint32_t b0 = __shfl_sync(0xffffffffu, pend_base, 0);
-        if (pend_emit) {
-            uint32_t j = b0 + __popc(pend_ballot & ((1u << lane) - 1u));
-            C.ray_o[j] = pend_o;
-            C.ray_d[j] = pend_d;
-            C.ray_x[j] = pend_x;
         }
     }
     flush_stat(C.stats, ST_FAILED, n_failed);

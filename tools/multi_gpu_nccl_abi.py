@@ -1,5 +1,5 @@
 """2+ GPU check of ipt_plane_allreduce (the C-ABI collective) with a raw ncclComm_t, without torch's collectives on
-the data path: `torchrun --nproc-per-node 2 tests/multi_gpu_nccl_abi.py`. torch.distributed (gloo) only ships the
+the data path: `torchrun --nproc-per-node 2 tools/multi_gpu_nccl_abi.py`. torch.distributed (gloo) only ships the
 ncclUniqueId to the other ranks. Each rank renders its pass range; after the all-reduce every rank must hold the
 single-GPU render of all passes."""
 import ctypes as C

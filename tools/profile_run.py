@@ -1,4 +1,4 @@
-"""Short run of the hot path for ncu: `python tests/profile_run.py [scene] [W] [H] [passes]`."""
+"""Short run of the hot path for ncu: `python tools/profile_run.py [scene] [W] [H] [passes]`."""
 import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from ipt_b200 import capi

@@ -1,5 +1,5 @@
 """Runs every BASELINE.json config briefly on one GPU and prints one JSON line per config (rates are pass-count
-independent). `python tests/run_configs.py [c1,c2,c3,c4,c5]`"""
+independent). `python tools/run_configs.py [c1,c2,c3,c4,c5]`"""
 import json, sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from ipt_b200 import capi

@@ -4,9 +4,9 @@ sys.path.insert(0, '.')
 from ipt_b200 import build
 variants = {
     "base": [],
-    "nodefer": ["IPT_DEFER_APPEND=0"],
+    
     "lights4": ["IPT_INLINE_LIGHTS=4"],
-    "nodefer_lights4": ["IPT_DEFER_APPEND=0", "IPT_INLINE_LIGHTS=4"],
+    
     "shade2": ["IPT_SHADE_MIN_BLOCKS=2"],
     "shade4": ["IPT_SHADE_MIN_BLOCKS=4"],
     "ext3": ["IPT_EXTEND_MIN_BLOCKS=3"],

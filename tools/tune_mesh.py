@@ -8,7 +8,7 @@ sel = sys.argv[1].split(",") if len(sys.argv) > 1 else list(variants)
 for name in sel:
     so = build.build_variant("mesh_" + name, variants[name])
     env = dict(os.environ, IPT_B200_LIB=str(so))
-    r = subprocess.run([sys.executable, "tests/run_configs.py", "c3_tree"], env=env, capture_output=True, text=True)
+    r = subprocess.run([sys.executable, "tools/run_configs.py", "c3_tree"], env=env, capture_output=True, text=True)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
         print(f"{name:14s} {d['mrays_per_s']:8.1f} Mrays/s  ext {d['ms_extend']:7.1f} ms", flush=True)
