@@ -184,6 +184,11 @@ int ipt_scene_desc_free(ipt_scene_desc* desc);
  * Light::area, power/area, and for area lights normalize(cross(x,y)). Host arithmetic in glm operation order. */
 int ipt_light_derived(const ipt_light* light, float* area, float* surface_power, float normal[3]);
 /* SimpleCamera::SimpleCamera (src/SimpleCamera.cpp:8-13) */
+/* The arrow keys of Gui::work (src/gui.cpp:105-134): LEFT/RIGHT orbit position and direction about the z axis by
+ * -/+ pi/12, DOWN/UP scale the position by 1.1 / (1/1.1); right and up are re-derived with the up hint (0,0,1).
+ * Host arithmetic in glm's operation order: bit-exact. */
+enum { IPT_KEY_LEFT = 0, IPT_KEY_RIGHT = 1, IPT_KEY_DOWN = 2, IPT_KEY_UP = 3 };
+int ipt_camera_orbit(ipt_camera* camera, int key);
 int ipt_camera_look(const float position[3], const float direction[3], const float up_hint[3], ipt_camera* out);
 
 /* ---- parity entry: Geometry::traceRay + Lighting::traceRayToLight + the light-vs-surface decision ---
@@ -247,6 +252,28 @@ int ipt_plane_device_ptrs(ipt_plane* plane, float** d_sum, float** d_sumsq, uint
 int ipt_plane_allreduce(ipt_plane* plane, void* nccl_comm);
 /* GridRenderPlane state after the same samples: pixels = sum/count, pixel_counters, max_value (GridRenderPlane.h:9-12). */
 int ipt_plane_resolve(ipt_plane* plane, float* pixels, uint64_t* pixel_counters, float* max_value);
+
+/* ---- the output stage: what Gui does with the accumulated image (src/gui.cpp) -------------------------
+ * All of it runs on the device; there is no CPU fallback (IPT_ERR_NO_DEVICE without a GPU). Images are row-major
+ * float32, `width*height` values, as CImg<float> stores them. */
+/* glare(image, cutoff), src/gui.cpp:38-52 with draw_halo :28-36 — the filter Gui::updateDisplay applies (:84): every
+ * pixel brighter than `cutoff` adds the halo 0.1*val/(0.25+r)^2 to every pixel; the sum is cut to [0, cutoff].
+ * Bit-exact. `n_bright` (may be NULL) receives the number of halo sources. */
+int ipt_image_glare(int device, const float* image, uint32_t width, uint32_t height, float cutoff, float* out, uint32_t* n_bright);
+/* normalize(image), src/gui.cpp:11-16: (image/max)^(1/2.2) cut to [0,1]. Within 1 ulp of the reference's powf. */
+int ipt_image_normalize(int device, const float* image, uint32_t width, uint32_t height, float* out);
+/* The pixel bytes of Gui::save (src/gui.cpp:192-194): normalize(image).normalize(0,255) truncated to 8 bits (CImg
+ * without libpng saves through an 8-bit PGM, include/CImg.h:60650-60667,59204-59209). Bit-exact. */
+int ipt_image_save_bytes(int device, const float* image, uint32_t width, uint32_t height, uint8_t* out);
+/* The same on a plane's accumulators (image = sum/count), without leaving the device:
+ * ipt_plane_display = what Gui::updateDisplay shows, normalize(glare(image, glare_cutoff)) (gui.cpp:83-87, no text overlay;
+ * Gui's default cutoff is 1.01, gui.h:24); `ms` (may be NULL) receives the device time of the filter chain.
+ * ipt_plane_save_bytes / ipt_plane_save_png = Gui::save. */
+int ipt_plane_display(ipt_plane* plane, float glare_cutoff, float* out, float* ms);
+int ipt_plane_save_bytes(ipt_plane* plane, uint8_t* out);
+int ipt_plane_save_png(ipt_plane* plane, const char* path);
+/* 8-bit greyscale PNG writer (host only; stored deflate blocks, no zlib dependency). */
+int ipt_write_png_gray8(const char* path, const uint8_t* bytes, uint32_t width, uint32_t height);
 
 /* ---- the hot path: replaces pass_count calls of render_sample (main.cpp:186-223) ------------------ */
 int ipt_render(ipt_scene* scene, ipt_plane* plane, const ipt_render_params* params, ipt_render_stats* stats);

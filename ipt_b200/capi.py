@@ -15,6 +15,7 @@ IPT_NO_HIT = 0xFFFFFFFF
 PLANE_GRID, PLANE_GUI, PLANE_LINEAR = 0, 1, 2
 FLAG_TIME_KERNELS, FLAG_KEEP_ZERO_WEIGHT, FLAG_DEBUG_PRINT, FLAG_RESOLVE_LAST_LEVEL = 1, 2, 4, 8
 STATUS = {0: "IPT_OK", 1: "IPT_ERR_INVALID", 2: "IPT_ERR_CUDA", 3: "IPT_ERR_NO_DEVICE", 4: "IPT_ERR_UNSUPPORTED", 5: "IPT_ERR_OVERFLOW"}
+IPT_ERR_INVALID = 1
 IPT_ERR_NO_DEVICE = 3
 
 import os
@@ -25,6 +26,7 @@ LIB_PATH = Path(os.environ.get("IPT_B200_LIB") or Path(__file__).resolve().paren
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
 
 
 class Material(C.Structure):
@@ -115,6 +117,14 @@ SIGNATURES = {
     "ipt_plane_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "ipt_plane_allreduce": (C.c_int, [_vp, _vp]),
     "ipt_plane_resolve": (C.c_int, [_vp, f32p, u64p, f32p]),
+    "ipt_image_glare": (C.c_int, [C.c_int, f32p, C.c_uint32, C.c_uint32, C.c_float, f32p, u32p]),
+    "ipt_image_normalize": (C.c_int, [C.c_int, f32p, C.c_uint32, C.c_uint32, f32p]),
+    "ipt_image_save_bytes": (C.c_int, [C.c_int, f32p, C.c_uint32, C.c_uint32, u8p]),
+    "ipt_plane_display": (C.c_int, [_vp, C.c_float, f32p, f32p]),
+    "ipt_plane_save_bytes": (C.c_int, [_vp, u8p]),
+    "ipt_plane_save_png": (C.c_int, [_vp, C.c_char_p]),
+    "ipt_write_png_gray8": (C.c_int, [C.c_char_p, u8p, C.c_uint32, C.c_uint32]),
+    "ipt_camera_orbit": (C.c_int, [C.POINTER(Camera), C.c_int]),
     "ipt_render": (C.c_int, [_vp, _vp, C.POINTER(RenderParams), C.POINTER(RenderStats)]),
     "ipt_render_host": (C.c_int, [_vp, C.POINTER(RenderParams), f32p, f32p, u32p, C.POINTER(RenderStats)]),
     "ipt_render_params_default": (None, [C.POINTER(RenderParams)]),
@@ -156,6 +166,38 @@ def _f32(a):
 
 def _ptr(a, t):
     return a.ctypes.data_as(t) if a is not None else None
+
+
+def image_glare(image, cutoff: float, device: int = 0):
+    """glare(image, cutoff) of gui.cpp:38-52 on the device; returns (filtered image, number of halo sources)."""
+    img = _f32(image); h, w = img.shape
+    out = np.empty_like(img); nb = C.c_uint32(0)
+    check(load().ipt_image_glare(device, _ptr(img, f32p), w, h, cutoff, _ptr(out, f32p), C.byref(nb)))
+    return out, nb.value
+
+
+def image_normalize(image, device: int = 0):
+    img = _f32(image); h, w = img.shape
+    out = np.empty_like(img)
+    check(load().ipt_image_normalize(device, _ptr(img, f32p), w, h, _ptr(out, f32p)))
+    return out
+
+
+def image_save_bytes(image, device: int = 0):
+    img = _f32(image); h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    check(load().ipt_image_save_bytes(device, _ptr(img, f32p), w, h, _ptr(out, u8p)))
+    return out
+
+
+def write_png_gray8(path, image_u8):
+    a = np.ascontiguousarray(image_u8, np.uint8); h, w = a.shape
+    check(load().ipt_write_png_gray8(str(path).encode(), _ptr(a, u8p), w, h))
+
+
+def camera_orbit(camera: Camera, key: int) -> Camera:
+    check(load().ipt_camera_orbit(C.byref(camera), key))
+    return camera
 
 
 def default_params(**kw) -> RenderParams:
@@ -340,6 +382,21 @@ class Plane:
         check(load().ipt_plane_resolve(self.handle, _ptr(pix, f32p), _ptr(cnt, u64p), C.byref(mx)))
         shape = (self.height, self.width)
         return pix.reshape(shape), cnt.reshape(shape), mx.value
+
+    def display(self, glare_cutoff: float = 1.01):
+        """What Gui::updateDisplay shows: normalize(glare(image, cutoff)) (gui.cpp:83-87); returns (image, device ms)."""
+        out = np.empty((self.height, self.width), np.float32); ms = C.c_float(0)
+        check(load().ipt_plane_display(self.handle, glare_cutoff, _ptr(out, f32p), C.byref(ms)))
+        return out, ms.value
+
+    def save_bytes(self):
+        """The pixel bytes of Gui::save (gui.cpp:192-194)."""
+        out = np.empty((self.height, self.width), np.uint8)
+        check(load().ipt_plane_save_bytes(self.handle, _ptr(out, u8p)))
+        return out
+
+    def save_png(self, path: str):
+        check(load().ipt_plane_save_png(self.handle, str(path).encode()))
 
     def close(self):
         if self.handle:

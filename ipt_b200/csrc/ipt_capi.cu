@@ -61,6 +61,26 @@ struct Workspace {
     size_t ray_cap = 0, hit_cap = 0, path_cap = 0;
 };
 
+// grow-only device scratch of the output stage (ipt_output.cuh): cudaMalloc/cudaFree per call would cost more than the
+// filters themselves
+struct GrowBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~GrowBuf() { cudaFree(p); }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+struct OutputScratch {
+    GrowBuf mean, glare, shown, bytes, rows, bright, small;
+};
+
 struct ipt_scene {
     // The reference calls render_sample from four threads on one Scene (main.cpp:258-277). One scene owns one stream and
     // one workspace, so every entry point that touches them takes this lock: concurrent callers are serialised.
@@ -85,6 +105,7 @@ struct ipt_scene {
     size_t pinned_bytes = 0;
     int grid_mesh = 0, grid_mesh_last = 0;
     int grid_generate = 0, grid_extend = 0, grid_extend_last = 0, grid_shade = 0, grid_accumulate = 0;
+    OutputScratch out;
 };
 
 struct ipt_plane {
@@ -1064,3 +1085,5 @@ int ipt_render_host(ipt_scene* s, const ipt_render_params* p, float* sum, float*
 }
 
 } // extern "C"
+
+#include "ipt_output.cuh"

@@ -309,6 +309,15 @@ void DeviceCamera::exportTo(SceneBuilder& b) const {
     put(b.camera.up, up);
     b.has_camera = true;
 }
+void DeviceCamera::orbit(int key) {
+    SceneBuilder b;
+    exportTo(b);
+    check(ipt_camera_orbit(&b.camera, key));
+    position = glm::vec3(b.camera.position[0], b.camera.position[1], b.camera.position[2]);
+    direction = glm::vec3(b.camera.direction[0], b.camera.direction[1], b.camera.direction[2]);
+    right = glm::vec3(b.camera.right[0], b.camera.right[1], b.camera.right[2]);
+    up = glm::vec3(b.camera.up[0], b.camera.up[1], b.camera.up[2]);
+}
 std::pair<glm::vec3, glm::vec3> DeviceCamera::sampleRay(float x, float y) const {
     SceneBuilder b;
     exportTo(b);
@@ -351,6 +360,16 @@ void DevicePlane::sums(std::vector<float>& sum, std::vector<float>& sumsq, std::
     sumsq.assign(width * height, 0.0f);
     count.assign(width * height, 0u);
     if (plane_) check(ipt_plane_download(plane_, sum.data(), sumsq.data(), count.data()));
+}
+std::vector<float> DevicePlane::display(float glare_cutoff) {
+    if (!plane_) throw Error{IPT_ERR_INVALID, "DevicePlane::display: nothing rendered yet"};
+    std::vector<float> out(width * height);
+    check(ipt_plane_display(plane_, glare_cutoff, out.data(), nullptr));
+    return out;
+}
+void DevicePlane::save(const char* path) {
+    if (!plane_) throw Error{IPT_ERR_INVALID, "DevicePlane::save: nothing rendered yet"};
+    check(ipt_plane_save_png(plane_, path));
 }
 void DevicePlane::download() {
     if (!plane_) return;

@@ -116,6 +116,8 @@ public:
     DeviceCamera(glm::vec3 position, glm::vec3 direction, glm::vec3 up_hint = glm::vec3(0, 0, 1));
     std::pair<glm::vec3, glm::vec3> sampleRay(float x, float y) const override;
     void exportTo(SceneBuilder& b) const override;
+    // the arrow keys of Gui::work (gui.cpp:105-134): IPT_KEY_LEFT / RIGHT orbit about z, IPT_KEY_DOWN / UP dolly by 1.1
+    void orbit(int key);
 
 private:
     mutable std::shared_ptr<DeviceContext> ctx_;
@@ -135,6 +137,10 @@ public:
     void addRay(float x, float y, float value) override; // one sample -> the device accumulators
     void download();                                     // refresh pixels / pixel_counters / max_value
     void sums(std::vector<float>& sum, std::vector<float>& sumsq, std::vector<uint32_t>& count);
+    // Gui's output stage on the device (gui.cpp): finalize/updateDisplay's image = normalize(glare(image, cutoff)), and
+    // save(path) = normalize(image).normalize(0,255) as an 8-bit PNG (Gui::save, gui.cpp:192-194)
+    std::vector<float> display(float glare_cutoff = 1.01f);
+    void save(const char* path);
 
     // used by render_sample: (re)attach to the device context of the scene being rendered
     ipt_plane* attach(const std::shared_ptr<DeviceContext>& ctx);

@@ -51,4 +51,23 @@ inline f33 inverse(const f33& m) {
     return r;
 }
 
+inline f3 operator*(const f33& m, f3 v) { // include/glm/detail/type_mat3x3.inl:468-474
+    return mk(m.c[0].x * v.x + m.c[1].x * v.y + m.c[2].x * v.z, m.c[0].y * v.x + m.c[1].y * v.y + m.c[2].y * v.z,
+              m.c[0].z * v.x + m.c[1].z * v.y + m.c[2].z * v.z);
+}
+// mat3(glm::rotate(identity<mat4>, angle, axis))            include/glm/ext/matrix_transform.inl:18-46
+inline f33 rotation(float angle, f3 v) {
+    float c = std::cos(angle), s = std::sin(angle);
+    f3 a = normalize(v), t = a * (1.0f - c);
+    float R[3][3];
+    R[0][0] = c + t.x * a.x; R[0][1] = t.x * a.y + s * a.z; R[0][2] = t.x * a.z - s * a.y;
+    R[1][0] = t.y * a.x - s * a.z; R[1][1] = c + t.y * a.y; R[1][2] = t.y * a.z + s * a.x;
+    R[2][0] = t.z * a.x + s * a.y; R[2][1] = t.z * a.y - s * a.x; R[2][2] = c + t.z * a.z;
+    f33 m; // Result[i] = I[0]*R[i][0] + I[1]*R[i][1] + I[2]*R[i][2]
+    for (int i = 0; i < 3; ++i)
+        m.c[i] = mk(1.0f * R[i][0] + 0.0f * R[i][1] + 0.0f * R[i][2], 0.0f * R[i][0] + 1.0f * R[i][1] + 0.0f * R[i][2],
+                    0.0f * R[i][0] + 0.0f * R[i][1] + 1.0f * R[i][2]);
+    return m;
+}
+
 } // namespace ipt_host

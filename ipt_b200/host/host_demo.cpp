@@ -4,6 +4,7 @@
 // calls through the Geometry / Lighting / Camera virtuals. Prints one JSON object; tests/test_gpu_host_cpp.py checks it.
 #include "device_plugins.hpp"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -49,7 +50,18 @@ int main(int argc, char** argv) {
         glm::vec3 smp = si ? si->sdf->sample() : glm::vec3();
         auto lddf = scene.lighting->distributionInPoint(glm::vec3(0.2f, -0.8f, -1.0f));
         float lval = lddf->value(glm::vec3(0, 0, 1));
+        // Gui's output stage (gui.cpp:186-194) and camera keys (gui.cpp:105-134) through the host classes
+        std::vector<float> shown = dplane.display(0.2f);
+        float shown_max = 0;
+        for (float v : shown) shown_max = v > shown_max ? v : shown_max;
+        if (argc > 3) dplane.save(argv[3]);
+        auto* cam = dynamic_cast<ipt_b200::DeviceCamera*>(const_cast<Camera*>(scene.camera.get()));
+        glm::vec3 before = cam->position;
+        cam->orbit(IPT_KEY_LEFT);
+        cam->orbit(IPT_KEY_RIGHT);
+        float orbit_err = std::fabs(cam->position.x - before.x) + std::fabs(cam->position.y - before.y) + std::fabs(cam->position.z - before.z);
         dplane.addRay(0.5f, 0.5f, 1.0f);
+        printf("{\"display_max\": %.9g, \"orbit_round_trip_error\": %.9g}\n", shown_max, orbit_err);
         printf("{\"scene\": \"%s\", \"paths\": %llu, \"rays\": %llu, \"mean_device_plane\": %.9g, \"count_device_plane\": %zu, "
                "\"mean_foreign_plane\": %.9g, \"cells_foreign_plane\": %zu, \"hit\": %d, \"hit_pos\": [%.9g, %.9g, %.9g], "
                "\"hit_normal\": [%.9g, %.9g, %.9g], \"sdf_value_at_normal\": %.9g, \"sdf_sample_dot_normal\": %.9g, \"light_hit\": %d, "

@@ -308,6 +308,32 @@ int ipt_camera_look(const float position[3], const float direction[3], const flo
     return IPT_OK;
 }
 
+// The arrow keys of Gui::work (src/gui.cpp:105-134): orbit about the z axis by pi/12, dolly by 1.1, then re-derive
+// right/up with the fixed up hint (0,0,1) (gui.cpp:130-131).
+int ipt_camera_orbit(ipt_camera* camera, int key) {
+    if (!camera) return IPT_ERR_INVALID;
+    f3 pos = mk(camera->position), dir = mk(camera->direction);
+    if (key == IPT_KEY_LEFT || key == IPT_KEY_RIGHT) {
+        float angle = key == IPT_KEY_LEFT ? (float)-M_PI / 12 : (float)+M_PI / 12; // gui.cpp:108,114
+        ipt_host::f33 mat = ipt_host::rotation(angle, mk(0, 0, 1));
+        pos = mat * pos;
+        dir = mat * dir;
+    } else if (key == IPT_KEY_DOWN) {
+        float f = static_cast<float>(1.1); // vec3 *= double casts the scalar first (type_vec3.inl:284-290)
+        pos = mk(pos.x * f, pos.y * f, pos.z * f);
+    } else if (key == IPT_KEY_UP) {
+        float f = static_cast<float>(1.1);
+        pos = mk(pos.x / f, pos.y / f, pos.z / f);
+    } else return IPT_ERR_INVALID;
+    f3 right = normalize(cross(dir, mk(0, 0, 1)));
+    f3 up = normalize(cross(right, dir));
+    put(camera->position, pos);
+    put(camera->direction, dir);
+    put(camera->right, right);
+    put(camera->up, up);
+    return IPT_OK;
+}
+
 int ipt_sample_scene(const char* name, ipt_scene_desc** out) {
     if (!name || !out) return IPT_ERR_INVALID;
     std::string n(name);

@@ -915,3 +915,4 @@ void ipt_oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint3
 }
 
 #include "ipt_oracle_mesh.inc"
+#include "ipt_oracle_output.inc"

@@ -10,6 +10,8 @@ Fixtures:
                      Lighting::traceRayToLight (hit, position, power), ray_power_preview, camera fields, light fields.
   ddf_kat.npz        Ddf::value known answers (src/libddf/test_ddf.cpp:181-223 and a direction sweep),
                      AreaLight KAT (src/lighting/test_lighting.cpp:130-144), GridRenderPlane::addRay KAT.
+  output_kat.npz     the output stage (src/gui.cpp): normalize(), glare(), the pixel bytes of Gui::save and the arrow-key
+                     camera orbit on two input images (`python tests/golden/make_golden.py output`).
   image_<scene>.npz  sum / sumsq / count of the reference estimator (ray_power_recursive, n_rays=16, depth_max=4)
                      over P passes at WxH with libc drand48, merged over forked workers seeded 1000+rank.
 """
@@ -117,6 +119,42 @@ def make_ddf_kat():
     print("ddf kat", {k: np.asarray(vv).shape for k, vv in out.items()})
 
 
+def output_inputs():
+    """Input images of the output-stage KAT (also used by the GPU tests): a synthetic HDR-like image with ragged size and the
+    committed reference render of the box scene (light visible -> real glare sources)."""
+    rng = np.random.default_rng(5)
+    a = (rng.random((48, 70)).astype(np.float32) ** 6 * np.float32(4.0)).astype(np.float32)
+    a[rng.random(a.shape) < 0.25] = 0
+    g = np.load(HERE / "image_box.npz")
+    b = (g["sum"] / np.maximum(g["count"], 1)).astype(np.float32)
+    b = np.ascontiguousarray(b[::2, 1::2][:61])  # 61x64 subsample keeps the bright light pixels
+    return {"synthetic": a, "box": b}
+
+
+def make_output_kat():
+    """Output stage (src/gui.cpp): normalize(), glare(), Gui::save bytes and the arrow-key camera orbit, from the compiled reference."""
+    import oracle_lib
+
+    ref = oracle_lib.load_ref()
+    out = {}
+    for name, img in output_inputs().items():
+        out[f"{name}_image"] = img
+        out[f"{name}_normalize"] = ref.image_normalize(img)
+        out[f"{name}_bytes"] = ref.image_save_bytes(img)
+        cut = [1.01, 0.25] if name == "synthetic" else [1.01, float(np.float32(img.max()) * np.float32(0.5))]
+        out[f"{name}_cutoffs"] = np.array(cut, np.float32)
+        out[f"{name}_glare"] = np.stack([ref.image_glare(img, c) for c in np.array(cut, np.float32)])
+        print(name, img.shape, "bright", [(img > c).sum() for c in cut])
+    keys = np.array([0, 0, 2, 1, 3, 3, 1, 1, 2, 0], np.int32)
+    cam = np.zeros((len(keys) + 1, 4, 3), np.float32)
+    pos, d = np.array([0.0, -3.0, 0.1], np.float32), np.array([0.0, 0.8111071, -0.5848977], np.float32)
+    cam[0, 0], cam[0, 1] = pos, d
+    for i, k in enumerate(keys):
+        cam[i + 1] = ref.camera_orbit(cam[i, 0], cam[i, 1], int(k))
+    out["orbit_keys"], out["orbit_cameras"] = keys, cam
+    np.savez_compressed(HERE / "output_kat.npz", **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "kats"):
@@ -124,3 +162,5 @@ if __name__ == "__main__":
         make_ddf_kat()
     if what in ("all", "images"):
         make_images()
+    if what in ("all", "kats", "output"):
+        make_output_kat()

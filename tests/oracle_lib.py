@@ -23,6 +23,7 @@ f64p = C.POINTER(C.c_double)
 u32p = C.POINTER(C.c_uint32)
 i32p = C.POINTER(C.c_int32)
 u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
 RNG_DRAND48, RNG_PHILOX = 0, 1
 
 
@@ -34,7 +35,8 @@ def _stale(target: Path, deps) -> bool:
 
 
 def build_oracle():
-    deps = [ROOT / "oracle" / "ipt_oracle.c", ROOT / "oracle" / "ipt_oracle_mesh.inc", ROOT / "include" / "ipt_b200.h"]
+    deps = [ROOT / "oracle" / "ipt_oracle.c", ROOT / "oracle" / "ipt_oracle_mesh.inc", ROOT / "oracle" / "ipt_oracle_output.inc",
+            ROOT / "include" / "ipt_b200.h"]
     if _stale(ORACLE_SO, deps):
         subprocess.run(["make", "-C", str(ROOT / "oracle"), "oracle"], check=True, capture_output=True)
     return ORACLE_SO
@@ -43,7 +45,7 @@ def build_oracle():
 def build_ref():
     """Compiles the reference where it lies; returns None if it is neither built nor buildable here."""
     if REF_SRC.exists():
-        if _stale(REF_SO, [ROOT / "oracle" / "ref_driver.cpp"]):
+        if _stale(REF_SO, [ROOT / "oracle" / "ref_driver.cpp", ROOT / "oracle" / "ref_gui_driver.cpp"]):
             subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref", f"REF={REF_SRC}"], check=True, capture_output=True)
     return REF_SO if REF_SO.exists() else None
 
@@ -69,7 +71,46 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-class Oracle:
+class _OutputStage:
+    """The output stage (src/gui.cpp) behind either checker: prefix 'ipt_oracle_' (restatement) or 'iptref_' (reference)."""
+    _prefix = ""
+
+    def _fn(self, name):
+        return getattr(self.lib, self._prefix + name)
+
+    def image_normalize(self, image):
+        img = _f32(image); h, w = img.shape
+        out = np.empty_like(img)
+        assert self._fn("image_normalize")(_p(img, f32p), C.c_uint32(w), C.c_uint32(h), _p(out, f32p)) == 0
+        return out
+
+    def image_glare(self, image, cutoff):
+        img = _f32(image); h, w = img.shape
+        out = np.empty_like(img)
+        assert self._fn("image_glare")(_p(img, f32p), C.c_uint32(w), C.c_uint32(h), C.c_float(cutoff), _p(out, f32p)) == 0
+        return out
+
+    def image_save_bytes(self, image):
+        img = _f32(image); h, w = img.shape
+        out = np.empty((h, w), np.uint8)
+        assert self._fn("image_save_bytes")(_p(img, f32p), C.c_uint32(w), C.c_uint32(h), _p(out, u8p)) == 0
+        return out
+
+    def camera_orbit(self, position, direction, key):
+        """Returns a (4,3) float32 array: position, direction, right, up after the key."""
+        cam = np.zeros((4, 3), np.float32)
+        cam[0], cam[1] = position, direction
+        if self._prefix == "iptref_":
+            assert self.lib.iptref_camera_orbit(_p(cam[0:1], f32p), C.cast(cam[1:2].ctypes.data, f32p), C.cast(cam[2:3].ctypes.data, f32p),
+                                                C.cast(cam[3:4].ctypes.data, f32p), key) == 0
+        else:
+            assert self.lib.ipt_oracle_camera_orbit(C.c_void_p(cam.ctypes.data), key) == 0  # ipt_camera == 12 floats
+        return cam
+
+
+class Oracle(_OutputStage):
+    _prefix = "ipt_oracle_"
+
     def __init__(self, lib):
         self.lib = lib
         lib.ipt_oracle_threads.restype = C.c_int
@@ -186,8 +227,9 @@ class Oracle:
         return list(out)
 
 
-class Ref:
-    """The compiled reference behind oracle/ref_driver.cpp."""
+class Ref(_OutputStage):
+    """The compiled reference behind oracle/ref_driver.cpp (main.cpp) and oracle/ref_gui_driver.cpp (gui.cpp)."""
+    _prefix = "iptref_"
 
     def __init__(self, lib):
         self.lib = lib

@@ -35,13 +35,20 @@ def test_host_classes_compile_against_the_reference_headers():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene", ["box", "cornell"])
-def test_render_sample_through_the_cpp_interfaces(scene, host_demo, oracle):
+def test_render_sample_through_the_cpp_interfaces(scene, host_demo, oracle, tmp_path):
     import oracle_lib
     from ipt_b200 import capi
 
-    r = subprocess.run([str(host_demo), scene, "4"], capture_output=True, text=True)
+    png = tmp_path / "result.png"
+    r = subprocess.run([str(host_demo), scene, "4", str(png)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    out = json.loads(r.stdout)
+    first, last = r.stdout.strip().splitlines()
+    stage = json.loads(first)
+    assert stage["display_max"] == 1.0 and stage["orbit_round_trip_error"] < 1e-5   # DevicePlane::display, DeviceCamera::orbit
+    from test_output_host import decode_png_gray8
+    img = decode_png_gray8(png.read_bytes())                                         # DevicePlane::save == Gui::save
+    assert img.shape == (96, 96) and img.max() == 255 and len(np.unique(img)) > 30
+    out = json.loads(last)
     assert out["paths"] == 96 * 96 * 4 and out["rays"] > out["paths"]
     sd = capi.SceneDescription(scene)
     p = capi.default_params(width=96, height=96, pass_count=4)
