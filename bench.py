@@ -287,7 +287,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     agg = dict(paths=0, rays=0, launches=0, ms_dev=0.0, ms_ext=0.0, ms_shade=0.0, ms_gen=0.0, ms_acc=0.0, n_ext=0, n_shade=0, queued=0,
-               surface=0, light=0, queue_bytes=0, nodes=0, tris=0)
+               surface=0, light=0, queue_bytes=0, nodes=0, tris=0, fused=0)
     sync()
     t0 = time.perf_counter()
     for s in range(args.steps):
@@ -295,7 +295,7 @@ def run_ours(args):
         agg["paths"] += st.paths; agg["rays"] += st.rays; agg["launches"] += st.kernel_launches; agg["ms_dev"] += st.ms_total
         agg["ms_ext"] += st.ms_extend; agg["ms_shade"] += st.ms_shade; agg["ms_gen"] += st.ms_generate; agg["ms_acc"] += st.ms_accumulate
         agg["n_ext"] += st.n_extend; agg["n_shade"] += st.n_shade; agg["surface"] += st.surface_hits; agg["light"] += st.light_hits
-        agg["queue_bytes"] += st.queue_bytes; agg["nodes"] += st.bvh_nodes_visited; agg["tris"] += st.triangles_tested
+        agg["queue_bytes"] += st.queue_bytes; agg["fused"] += st.rays_resolved_in_shade; agg["nodes"] += st.bvh_nodes_visited; agg["tris"] += st.triangles_tested
     if world > 1:  # the only collective of the path: reduce the accumulators over NVLink
         dist.all_reduce(acc_sum); dist.all_reduce(acc_sq); dist.all_reduce(acc_cnt)
     sync()
@@ -340,11 +340,17 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel and its algorithmic bytes: ray records are 36 B, hit records 32 B
+        # dominant kernel and its algorithmic bytes: the wavefront MODEL of SURVEY.md §8d — every ray
+        # is a 36 B record written once and read once, every queued hit a 32 B record written once and read once.
+        # The fused shade kernel resolves the last traced depth without queueing it: it is credited with the model bytes
+        # of the two kernels it replaces (36 B write + 36 B read per such ray + 8 B per light hit), and
+        # `implemented_bytes_per_launch` says what the implementation itself has to move.
         children = agg["rays"] - agg["paths"]
         queued = (agg["queue_bytes"] - 72 * agg["rays"] - 8 * agg["paths"]) // 64
-        bytes_ext = 36 * agg["rays"] + 32 * queued + 8 * agg["light"] + 64 * (agg["nodes"] + agg["tris"])  # + BVH nodes / triangle records
-        bytes_shade = 32 * queued + 36 * children
+        fused = agg["fused"]
+        bytes_ext = 36 * (agg["rays"] - fused) + 32 * queued + 8 * agg["light"] + 64 * (agg["nodes"] + agg["tris"])  # + BVH nodes / triangle records
+        bytes_shade = 32 * queued + 36 * children + 36 * fused
+        bytes_shade_impl = 32 * queued + 36 * (children - fused)
         dom = "shade" if agg["ms_shade"] >= agg["ms_ext"] else "extend"
         dom_ms = agg["ms_shade"] if dom == "shade" else agg["ms_ext"]
         dom_n = agg["n_shade"] if dom == "shade" else agg["n_ext"]
@@ -364,7 +370,7 @@ def run_ours(args):
             "config": {"workload": workload_text(), "passes_per_step": pps, "paths_per_step_per_gpu": paths_per_pass * pps,
                        "parallelism": f"pass-sharded x{world}" if world > 1 else "single GPU",
                        "l2": "per-step ray/hit queue working set (>1 GB) exceeds the 126 MB L2; no flush needed",
-                       "batch_paths": args.batch_paths or (1 << 19)},
+                       "batch_paths": args.batch_paths or "library default (2^27 / widest queued tree level)"},
             "mrays_per_s": rays_all / elapsed / 1e6, "rays_per_path": rays_all / max(paths_all, 1), "image_mean": image_mean,
             "device_ms_per_step": agg["ms_dev"] / args.steps,
             "clocks": clocks,
@@ -375,6 +381,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": ("k_extend_mesh" if dom == "extend" and w["scene"].startswith("mesh") else f"k_{dom}"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "launches": dom_n, "avg_launch_ms": dom_ms / max(dom_n, 1),
                          "algorithmic_bytes_per_launch": dom_bytes / max(dom_n, 1),
+                         "implemented_bytes_per_launch": (bytes_shade_impl if dom == "shade" else bytes_ext) / max(dom_n, 1),
+                         "model": "SURVEY 8d wavefront queue model: 36 B ray record written + read per ray, 32 B hit record written + read per queued hit",
                          "whole_pipeline": {"bytes": agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"]),
                                             "achieved_gbs": (agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"])) / (agg["ms_dev"] * 1e-3) / 1e9,
                                             "frac": (agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"])) / (agg["ms_dev"] * 1e-3) / 1e9 / peak},

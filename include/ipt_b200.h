@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IPT_B200_ABI_VERSION 1
+#define IPT_B200_ABI_VERSION 2
 #define IPT_MAX_DEPTH 16
 #define IPT_NO_HIT 0xFFFFFFFFu
 
@@ -127,7 +127,11 @@ enum ipt_render_flags {
     /* At the last traced depth a ray only matters if it reaches a light, so by default the geometry is intersected
      * only for rays that hit a light ("shadow ray"); with this flag every last-level ray is resolved into
      * surface hit / miss as well, which only affects ipt_render_stats::surface_hits / misses. */
-    IPT_FLAG_RESOLVE_LAST_LEVEL = 8u
+    IPT_FLAG_RESOLVE_LAST_LEVEL = 8u,
+    /* Analytic scenes resolve the last traced depth inside the shade kernel that spawns it (the rays of the widest
+     * tree level are never queued). This flag keeps them on the queue + k_extend<LAST> path; results are the same up to
+     * the order of the float atomics. */
+    IPT_FLAG_NO_FUSED_LAST_LEVEL = 16u
 };
 
 typedef struct ipt_render_params {
@@ -156,7 +160,10 @@ typedef struct ipt_render_stats {
     float ms_total;                    /* device time of the whole call (CUDA events) */
     float ms_generate, ms_extend, ms_shade, ms_accumulate; /* with IPT_FLAG_TIME_KERNELS */
     uint32_t n_extend, n_shade;        /* launches summed into ms_extend / ms_shade */
-    uint64_t queue_bytes;              /* bytes of ray/hit queue records written + read */
+    uint64_t queue_bytes;              /* queue traffic of the wavefront MODEL: 72 B per ray (36 B record written
+                                        * + read), 64 B per queued surface hit, 8 B per path */
+    uint64_t rays_resolved_in_shade;   /* rays of the last traced depth that the fused shade kernel resolved without queueing
+                                        * them: the implementation moves queue_bytes - 72 * this */
 } ipt_render_stats;
 
 typedef struct ipt_scene ipt_scene; /* opaque: device copy of the scene (+ LBVH) */

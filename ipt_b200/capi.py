@@ -13,7 +13,7 @@ import numpy as np
 IPT_MAX_DEPTH = 16
 IPT_NO_HIT = 0xFFFFFFFF
 PLANE_GRID, PLANE_GUI, PLANE_LINEAR = 0, 1, 2
-FLAG_TIME_KERNELS, FLAG_KEEP_ZERO_WEIGHT, FLAG_DEBUG_PRINT, FLAG_RESOLVE_LAST_LEVEL = 1, 2, 4, 8
+FLAG_TIME_KERNELS, FLAG_KEEP_ZERO_WEIGHT, FLAG_DEBUG_PRINT, FLAG_RESOLVE_LAST_LEVEL, FLAG_NO_FUSED_LAST_LEVEL = 1, 2, 4, 8, 16
 STATUS = {0: "IPT_OK", 1: "IPT_ERR_INVALID", 2: "IPT_ERR_CUDA", 3: "IPT_ERR_NO_DEVICE", 4: "IPT_ERR_UNSUPPORTED", 5: "IPT_ERR_OVERFLOW"}
 IPT_ERR_INVALID = 1
 IPT_ERR_NO_DEVICE = 3
@@ -67,7 +67,8 @@ class RenderStats(C.Structure):
                 ("bvh_nodes_visited", C.c_uint64), ("triangles_tested", C.c_uint64), ("lights_tested", C.c_uint64),
                 ("batches", C.c_uint32), ("kernel_launches", C.c_uint32), ("ms_total", C.c_float),
                 ("ms_generate", C.c_float), ("ms_extend", C.c_float), ("ms_shade", C.c_float), ("ms_accumulate", C.c_float),
-                ("n_extend", C.c_uint32), ("n_shade", C.c_uint32), ("queue_bytes", C.c_uint64)]
+                ("n_extend", C.c_uint32), ("n_shade", C.c_uint32), ("queue_bytes", C.c_uint64),
+                ("rays_resolved_in_shade", C.c_uint64)]
 
     def as_dict(self):
         d = {}

@@ -104,7 +104,7 @@ struct ipt_scene {
     float* pinned = nullptr;         // staging for ipt_render_host
     size_t pinned_bytes = 0;
     int grid_mesh = 0, grid_mesh_last = 0;
-    int grid_generate = 0, grid_extend = 0, grid_extend_last = 0, grid_shade = 0, grid_accumulate = 0;
+    int grid_generate = 0, grid_extend = 0, grid_extend_last = 0, grid_shade = 0, grid_shade_fused = 0, grid_accumulate = 0;
     OutputScratch out;
 };
 
@@ -521,7 +521,8 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
 
     size_t sm = stack_smem(s);
     s->grid_generate = occupancy_grid(k_generate, s->sm_count, 0);
-    s->grid_shade = occupancy_grid(k_shade, s->sm_count, 0);
+    s->grid_shade = occupancy_grid(k_shade<false, false>, s->sm_count, 0);
+    s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<true, true>, s->sm_count, 0) : occupancy_grid(k_shade<true, false>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
         s->grid_mesh = occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
@@ -914,12 +915,16 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     if (p->plane_mode > IPT_PLANE_LINEAR) return fail(IPT_ERR_INVALID, "unknown plane mode");
     CUDA_TRY(cudaSetDevice(s->device));
 
+    const bool fuse_last = !s->mesh && !(p->flags & (IPT_FLAG_DEBUG_PRINT | IPT_FLAG_RESOLVE_LAST_LEVEL | IPT_FLAG_NO_FUSED_LAST_LEVEL));
     // widest tree level among traced depths -> bits for the node index inside the ray tag
     uint64_t width_at[IPT_MAX_DEPTH];
-    uint64_t w = 1, max_ray_w = 1, max_hit_w = 1;
+    uint64_t w = 1, max_ray_w = 1, max_hit_w = 1, max_queued_w = 1;
     for (uint32_t d = 0; d < p->depth_max; ++d) {
         width_at[d] = w;
         max_ray_w = std::max(max_ray_w, w);
+        // with the fused last level the rays of the last traced depth (> 0) are never queued
+        bool is_last = d + 1 == p->depth_max || p->schedule[d] == 0;
+        if (!(fuse_last && is_last && d > 0)) max_queued_w = std::max(max_queued_w, w);
         if (d + 1 < p->depth_max) max_hit_w = std::max(max_hit_w, w);
         w *= p->schedule[d];
         if (w > (1ull << 31)) return fail(IPT_ERR_UNSUPPORTED, "split schedule too wide (more than 2^31 nodes per tree level)");
@@ -934,12 +939,14 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     uint64_t total_paths = (uint64_t)tw * th * p->pass_count;
     // default batch: as many paths as keep the widest tree level near 2^28 rays (2^19 paths at 16/8/4/2; up to 2^23
     // for narrow schedules such as depth 8 with one child per hit, whose deeper levels would otherwise be tiny launches)
-    uint64_t batch = p->batch_paths ? p->batch_paths : std::min<uint64_t>(1ull << 23, std::max<uint64_t>(1ull << 16, (1ull << 28) / max_ray_w));
+    // (with the fused last level the widest level is not queued: 2^27 / widest queued level, i.e. 2^20 paths at 16/8/4/2)
+    uint64_t batch_rays = max_queued_w < max_ray_w ? (1ull << 27) : (1ull << 28);
+    uint64_t batch = p->batch_paths ? p->batch_paths : std::min<uint64_t>(1ull << 23, std::max<uint64_t>(1ull << 16, batch_rays / max_queued_w));
     batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
     const uint64_t budget = 24ull << 30; // bytes of queue memory
-    while (batch > 1024 && batch * (max_ray_w * 36 + max_hit_w * 32) > budget) batch >>= 1;
+    while (batch > 1024 && batch * (max_queued_w * 36 + max_hit_w * 32) > budget) batch >>= 1;
     batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(total_paths, 1)));
-    int rc = ensure_workspace(s, batch * max_ray_w, batch * max_hit_w, batch);
+    int rc = ensure_workspace(s, batch * max_queued_w, batch * max_hit_w, batch);
     if (rc) return rc;
 
     RenderCtx C;
@@ -1001,7 +1008,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 }
                 TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
                 int gs2 = std::max(1, std::min(s->grid_shade, cap_blocks));
-                TIMED(2, (k_shade<<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                TIMED(2, (k_shade<false, false><<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 continue;
             }
             if (last) {
@@ -1015,8 +1022,17 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
 #define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
             DISPATCH_SM(s, CALL);
 #undef CALL
+            // the children of this level are the last traced depth: resolve them inside the shade kernel (no queue, no
+            // k_extend<LAST> launch); analytic scenes only, and not when a flag asks for the unfused behaviour
+            bool child_last = width_at[d + 1] != 0 && ((d + 2 == p->depth_max) || p->schedule[d + 1] == 0);
+            if (child_last && fuse_last) {
+                int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
+                if (s->smallpt) TIMED(2, (k_shade<true, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<true, false><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                break;
+            }
             int gs = std::max(1, std::min(s->grid_shade, cap_blocks));
-            TIMED(2, (k_shade<<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+            TIMED(2, (k_shade<false, false><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
         }
         TIMED(3, (k_accumulate<<<std::max(1, gg), IPT_BLOCK, 0, s->stream>>>(C)));
 #undef TIMED
@@ -1061,6 +1077,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
         }
         // ray record written + read (2 x 36 B) per ray, hit record written + read per QUEUED surface hit, pathval RMW
         stats->queue_bytes = 72ull * stats->rays + 64ull * h[ST_QUEUED] + 8ull * stats->paths;
+        stats->rays_resolved_in_shade = h[ST_FUSED];
     }
     return IPT_OK;
 }

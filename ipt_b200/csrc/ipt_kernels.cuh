@@ -20,6 +20,9 @@
 #ifndef IPT_SHADE_MIN_BLOCKS
 #define IPT_SHADE_MIN_BLOCKS 2
 #endif
+#ifndef IPT_SHADE_FUSED_MIN_BLOCKS
+#define IPT_SHADE_FUSED_MIN_BLOCKS 3 // 80 registers, 156 B of spills: still 4 % faster than 2 blocks (profiles/tuning_r01.md)
+#endif
 #ifndef IPT_EXTEND_MIN_BLOCKS
 #define IPT_EXTEND_MIN_BLOCKS 3
 #endif
@@ -28,7 +31,7 @@
 namespace iptd {
 
 enum StatSlot {
-    ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED,
+    ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED, ST_FUSED,
     ST_RAYS_AT_DEPTH = 16, // + depth
     ST_COUNT = 16 + IPT_MAX_DEPTH
 };
@@ -398,9 +401,36 @@ __device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, 
     }
 }
 
+#ifndef IPT_PARK
+#define IPT_PARK 64 // entries per warp: fewer than 32 are parked when up to 32 more arrive
+#endif
+// Second half of trace_scene_last for a parked ray that reached a light at `lpos`: Geometry::traceRay and the
+// light-vs-surface decision of main.cpp:113; the light's contribution is added if nothing is nearer.
+template <bool SMALLPT>
+__device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, TraceCounters& tc,
+                                               uint32_t& n_light, uint32_t& n_surface) {
+    f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
+    f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
+    f3 lpos = mk3(dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], dq[8 * IPT_PARK + k]);
+    SurfHit sh = trace_geometry<SMALLPT, false>(S, o, d, tc);
+    bool light_wins = sh.prim == IPT_NO_HIT;
+    if (!light_wins) {
+        f3 sp = xpoint(o, d, sh.t);
+        light_wins = xlength3(xsub3(sp, o)) > xlength3(xsub3(lpos, o));
+    }
+    if (light_wins) {
+        ++n_light;
+        atomicAdd(&C.pathval[__float_as_uint(dq[10 * IPT_PARK + k])], dq[9 * IPT_PARK + k]);
+    } else ++n_surface;
+}
+
 // K3 shade: one thread per surface hit; spawns schedule[depth] children from the 1:1 mixture of the light DDF
 // and the surface DDF (main.cpp:142-177) and appends the survivors to the ray queue of depth+1.
-__global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+// FUSE_LAST (analytic scenes, children are the last traced depth): the children are "shadow rays" (see
+// trace_scene_last), so instead of being queued for k_extend<LAST> they are resolved right here — same functions, same
+// operands, same counters; the widest level of the tree never touches memory.
+template <bool FUSE_LAST, bool SMALLPT>
+__global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : IPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth + 1];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -408,6 +438,11 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
     const uint32_t n_children = C.schedule[depth];
     const float inv_n = 1.0f / (float)n_children;
     uint32_t n_failed = 0, n_pruned = 0, n_dropped = 0;
+    uint32_t n_fused = 0, n_light = 0, n_surface = 0;
+    TraceCounters tc{0, 0};
+    __shared__ float dq_all[FUSE_LAST ? (256 / 32) * 11 * IPT_PARK : 1];
+    float* dq = dq_all + (FUSE_LAST ? (threadIdx.x >> 5) * 11 * IPT_PARK : 0); // this warp's parked occlusion tests
+    uint32_t qn = 0;                                                            // warp-uniform
     uint32_t* out_count = &C.cnt[2 * (depth + 1)];
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
         uint32_t i = base + lane;
@@ -477,6 +512,45 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
                     }
                 }
             }
+            if (FUSE_LAST) {
+                // the body of k_extend<LAST> for this ray, in two steps: the light test now; the occlusion test of the
+                // rays that did reach a light (about a third) is parked in a per-warp shared-memory queue and run 32 at a
+                // time, so the geometry intersection is issued for full warps instead of for the third of the lanes
+                bool park = false;
+                float contrib = 0.0f;
+                f3 lpos = mk3(0, 0, 0);
+                if (emit) {
+                    ++n_fused;
+                    uint32_t li = IPT_NO_HIT;
+                    bool lh = trace_lights(S, pos, w, li, lpos);
+                    float wr = resolve_weight(S, wgt, child_sv, pos, lh, lpos);
+                    if (!isfinite(wr)) ++n_dropped;
+                    else if (lh) {
+                        float power = S.light_inline ? S.lights[li].surface_power : S.lights_g[li].surface_power;
+                        if (!isfinite(power)) power = 1.0f; // main.cpp:123 point-light hack
+                        contrib = wr * power;
+                        park = true;
+                    }
+                }
+                uint32_t pb = __ballot_sync(0xffffffffu, park);
+                if (pb) {
+                    if (park) {
+                        uint32_t k = qn + __popc(pb & ((1u << lane) - 1u));
+                        dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
+                        dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
+                        dq[6 * IPT_PARK + k] = lpos.x; dq[7 * IPT_PARK + k] = lpos.y; dq[8 * IPT_PARK + k] = lpos.z;
+                        dq[9 * IPT_PARK + k] = contrib; dq[10 * IPT_PARK + k] = __uint_as_float(tag & C.slot_mask);
+                    }
+                    qn += __popc(pb);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        qn -= 32;
+                        resolve_parked<SMALLPT>(S, C, dq, qn + lane, tc, n_light, n_surface);
+                        __syncwarp();
+                    }
+                }
+                continue;
+            }
             // warp-aggregated append (see k_extend)
             uint32_t ballot = __ballot_sync(0xffffffffu, emit);
             if (ballot) {
@@ -493,9 +567,20 @@ __global__ void __launch_bounds__(256, IPT_SHADE_MIN_BLOCKS) k_shade(const __gri
             }
         }
     }
+    if (FUSE_LAST && lane < qn) resolve_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface); // drain
     flush_stat(C.stats, ST_FAILED, n_failed);
     flush_stat(C.stats, ST_PRUNED, n_pruned);
     flush_stat(C.stats, ST_DROPPED, n_dropped);
+    if (FUSE_LAST) {
+        flush_stat(C.stats, ST_LIGHT, n_light);
+        flush_stat(C.stats, ST_SURFACE, n_surface);
+        // rays of depth+1 that were traced without being queued: k_accumulate folds cnt[] into the per-depth ray counts
+        for (int off = 16; off > 0; off >>= 1) n_fused += __shfl_down_sync(0xffffffffu, n_fused, off);
+        if (lane == 0 && n_fused) {
+            atomicAdd(out_count, n_fused);
+            atomicAdd(&C.stats[ST_FUSED], (unsigned long long)n_fused);
+        }
+    }
 }
 
 // accumulator cell of a sample: GridRenderPlane::addRay (src/GridRenderPlane.cpp:66-67), Gui::addRay (gui.cpp:168-172)

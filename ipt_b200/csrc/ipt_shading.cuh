@@ -87,12 +87,17 @@ __device__ __forceinline__ float base_value(int kind, float z) {
     return ((float)kind + 1.0f) * ipow(z, kind) * (0.5f / IPT_PI_F);
 }
 
-// The surface DDF of a hit: RotateDdf(CosineDdf, normal) or the glossy extension.
+// The surface DDF of a hit: RotateDdf(CosineDdf, normal) or the glossy extension. Both are members of one family —
+// kd * PowerCosine(1) about the normal + ks * PowerCosine(n) about the mirror direction, with kd = 1, ks = 0 for the
+// Lambert case — and are evaluated by ONE branch-free code path: hits of both materials share warps at every depth
+// after the first, so a per-material branch would issue both sides for nearly every warp.
 struct Sdf {
     uint32_t ddf;
     f3 normal, refl;
     float wd, ws;
-    int exponent;
+    float exponent;   // n of the lobe (1 for Lambert: unused, ks = 0)
+    float inv_np1;    // 1 / (n + 1): the sampling exponent of the lobe
+    float lobe_norm;  // (n + 1) / (2 pi)
 };
 __device__ __forceinline__ f3 reflect3(f3 I, f3 N) { // glm::reflect: I - N*dot(N,I)*2
     float k = 2.0f * dot3(N, I);
@@ -100,28 +105,42 @@ __device__ __forceinline__ f3 reflect3(f3 I, f3 N) { // glm::reflect: I - N*dot(
 }
 __device__ __forceinline__ Sdf make_sdf(const DevMaterial& m, f3 normal, f3 dir_in) {
     Sdf s;
+    bool glossy = m.ddf == IPT_DDF_GLOSSY;
     s.ddf = m.ddf;
     s.normal = normal;
-    s.wd = m.wd; s.ws = m.ws;
-    s.exponent = (int)m.exponent;
-    s.refl = m.ddf == IPT_DDF_GLOSSY ? reflect3(dir_in, normal) : normal;
+    s.wd = glossy ? m.wd : 1.0f;
+    s.ws = glossy ? m.ws : 0.0f;
+    s.exponent = glossy ? (float)(int)m.exponent : 1.0f;
+    s.inv_np1 = 1.0f / (s.exponent + 1.0f);
+    s.lobe_norm = (s.exponent + 1.0f) * (0.5f / IPT_PI_F);
+    s.refl = glossy ? reflect3(dir_in, normal) : normal;
     return s;
 }
+// Lambert: z/pi (ddf.cpp:104-108); glossy: kd*z/pi + ks*(n+1)/(2 pi)*cos^n about the mirror direction, 0 below the surface
 __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
     float cn = dot3(s.normal, w);
-    if (s.ddf == IPT_DDF_COSINE) return base_value(2, cn);
-    if (cn < 0.0f) return 0.0f;
-    return s.wd * base_value(2, cn) + s.ws * base_value(s.exponent, dot3(s.refl, w));
+    float zr = dot3(s.refl, w);
+    float lobe = zr > 0.0f ? exp2f(s.exponent * log2f(zr)) : 0.0f;
+    float v = s.wd * (cn * (1.0f / IPT_PI_F)) + s.ws * (s.lobe_norm * lobe);
+    return cn < 0.0f ? 0.0f : v;
 }
 // zero vector == failed sample. ul is the lobe-selection draw (ROLE_LOBE in the oracle).
-// bl: basis about the mirror direction (glossy hits only; built once per hit, not per child)
+// bl: basis about the mirror direction (== bn for Lambert hits; built once per hit, not per child)
 __device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, const Basis& bl, float u1, float u2, float ul) {
-    if (s.ddf == IPT_DDF_COSINE) return rotate(bn, base_sample(2, u1, u2));
-    f3 w;
-    if (ul < s.wd) w = rotate(bn, base_sample(2, u1, u2));
-    else w = rotate(bl, base_sample(s.exponent, u1, u2));
-    if (dot3(s.normal, w) < 0.0f) return mk3(0, 0, 0);
-    return w;
+    bool lobe = !(ul < s.wd);               // never for Lambert (wd = 1 > ul)
+    float e = lobe ? s.inv_np1 : 0.5f;      // cos(alpha) = u1^(1/(n+1)); sqrt(u1) for the cosine DDF (ddf.cpp:94)
+    float zc = exp2f(__log2f(u1) * e);      // u1 = 0 -> 0
+    float r = fsqrt(fmaxf(0.0f, 1.0f - zc * zc));
+    float a = (2.0f * u2 - 1.0f) * IPT_PI_F; // see base_sample
+    float sp = -__sinf(a), cp = -__cosf(a);
+    f3 x = mk3(r * cp, r * sp, zc);
+    Basis b;
+    b.c0 = lobe ? bl.c0 : bn.c0;
+    b.c1 = lobe ? bl.c1 : bn.c1;
+    b.c2 = lobe ? bl.c2 : bn.c2;
+    f3 w = rotate(b, x);
+    bool below = s.ddf == IPT_DDF_GLOSSY && dot3(s.normal, w) < 0.0f;
+    return below ? mk3(0, 0, 0) : w;
 }
 
 // DdfFromLight::value (src/lighting/lighting.cpp:61-73)

@@ -113,6 +113,26 @@ def test_zero_weight_pruning_preserves_the_image(scenes):
     assert a[3].rays <= b[3].rays and a[3].zero_weight_pruned > 0
 
 
+@pytest.mark.parametrize("name,kw", [("box", {}), ("cornell", {}), ("smallpt", {}), ("mixedlights", {}), ("lightgrid:3x3", {}),
+                                     ("box", dict(depth_max=2, schedule=[5, 3])), ("box", dict(depth_max=1)),
+                                     ("cornell", dict(depth_max=3, schedule=[4, 0, 2]))])
+def test_fused_last_level_equals_queued_last_level(name, kw, scenes):
+    """The shade kernel that resolves its own children (default on analytic scenes) against the queue + k_extend<LAST>
+    path (IPT_FLAG_NO_FUSED_LAST_LEVEL): same rays, same hits; sums equal up to the order of the float atomics."""
+    sd, sc = scenes(name)
+    base = dict(width=64, height=64, pass_count=3, plane_mode=capi.PLANE_LINEAR)
+    base.update(kw)
+    a = sc.render_host(capi.default_params(**base))
+    b = sc.render_host(capi.default_params(flags=capi.FLAG_NO_FUSED_LAST_LEVEL, **base))
+    assert np.allclose(a[0], b[0], rtol=2e-5, atol=1e-7) and np.allclose(a[1], b[1], rtol=5e-5, atol=1e-7)
+    assert np.array_equal(a[2], b[2])
+    for f in ("rays", "light_hits", "surface_hits", "misses", "failed_samples", "zero_weight_pruned", "nonfinite_dropped"):
+        assert getattr(a[3], f) == getattr(b[3], f), f
+    assert list(a[3].rays_at_depth) == list(b[3].rays_at_depth)
+    if base.get("depth_max", 4) >= 2 and base.get("schedule", [1])[-1] != 0:
+        assert a[3].kernel_launches < b[3].kernel_launches
+
+
 def test_batching_and_tiles_are_invisible(scenes):
     """Philox counters are keyed by (pixel, pass, node): batch size, tiles and pass ranges must not change the result."""
     sd, sc = scenes("box")

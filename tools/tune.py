@@ -4,16 +4,14 @@ sys.path.insert(0, '.')
 from ipt_b200 import build
 variants = {
     "base": [],
-    
+    "fused3": ["IPT_SHADE_FUSED_MIN_BLOCKS=3"],
+    "fused4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
+    "fused3_ext4": ["IPT_SHADE_FUSED_MIN_BLOCKS=3", "IPT_EXTEND_MIN_BLOCKS=4"],
+    "fused3_shade3": ["IPT_SHADE_FUSED_MIN_BLOCKS=3", "IPT_SHADE_MIN_BLOCKS=3"],
     "lights4": ["IPT_INLINE_LIGHTS=4"],
-    
-    "shade2": ["IPT_SHADE_MIN_BLOCKS=2"],
-    "shade4": ["IPT_SHADE_MIN_BLOCKS=4"],
-    "ext3": ["IPT_EXTEND_MIN_BLOCKS=3"],
-    "nd_s2_e3": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=2", "IPT_EXTEND_MIN_BLOCKS=3"],
-    "nd_s2_e2": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=2", "IPT_EXTEND_MIN_BLOCKS=2"],
-    "nd_s1_e3": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=1", "IPT_EXTEND_MIN_BLOCKS=3"],
-    "nd_s3_e3": ["IPT_DEFER_APPEND=0", "IPT_SHADE_MIN_BLOCKS=3", "IPT_EXTEND_MIN_BLOCKS=3"],
+    "shade3": ["IPT_SHADE_MIN_BLOCKS=3"],
+    "ext2": ["IPT_EXTEND_MIN_BLOCKS=2"],
+    "ext4": ["IPT_EXTEND_MIN_BLOCKS=4"],
 }
 sel = sys.argv[1].split(",") if len(sys.argv) > 1 else list(variants)
 batches = [int(b) for b in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0"])]
