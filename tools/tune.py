@@ -4,6 +4,7 @@ sys.path.insert(0, '.')
 from ipt_b200 import build
 variants = {
     "base": [],
+    "fused2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2"],
     "fused3": ["IPT_SHADE_FUSED_MIN_BLOCKS=3"],
     "fused4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
     "fused3_ext4": ["IPT_SHADE_FUSED_MIN_BLOCKS=3", "IPT_EXTEND_MIN_BLOCKS=4"],
