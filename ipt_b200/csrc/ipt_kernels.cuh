@@ -30,6 +30,8 @@
 
 namespace iptd {
 
+enum LightQuery { LQ_PDF = 0, LQ_NEAREST = 1, LQ_BOTH = 2 };
+
 enum StatSlot {
     ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED, ST_FUSED,
     ST_RAYS_AT_DEPTH = 16, // + depth
@@ -146,8 +148,9 @@ template <bool SMALLPT, bool MESH>
 __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc);
 
 // ---- nearest light (CollectionLighting::traceRayToLight, src/CollectionLighting.cpp:23-34) -----------
-template <class LightRef>
-__device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f3 o, f3 d, bool& any, float& best_len, uint32_t& which, f3& lpos) {
+template <bool PDF, class LightRef>
+__device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f3 o, f3 d, bool& any, float& best_len, uint32_t& which, f3& lpos,
+                                                float& lpdf) {
     LightHit e = light_trace(L, o, d);
     if (!e.hit) return;
     float len = xlength3(xsub3(e.position, o));
@@ -157,6 +160,7 @@ __device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f
         which = i;
         lpos = e.position;
     }
+    if (PDF) lpdf += L.weight * light_pdf_at(L, o, e.position);
 }
 // conservative ray/box test for the light LBVH (see slab() in ipt_trace.cuh); limit = farthest useful entry distance
 __device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, float limit) {
@@ -169,10 +173,13 @@ __device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, f
 }
 
 // One stack traversal of the light LBVH serving both queries of CollectionLighting:
-//   NEAREST: traceRayToLight (CollectionLighting.cpp:23-34): nearest hit by length(pos - origin), earliest index on ties
-//   !NEAREST: the mixture density sum_i w_i * DdfFromLight_i::value(d) over ALL lights the ray hits (ddf.cpp:156-162)
-template <bool NEAREST>
+//   LQ_NEAREST: traceRayToLight (CollectionLighting.cpp:23-34): nearest hit by length(pos - origin), earliest index on ties
+//   LQ_PDF:     the mixture density sum_i w_i * DdfFromLight_i::value(d) over ALL lights the ray hits (ddf.cpp:156-162)
+//   LQ_BOTH:    both from one traversal (returns the density; the nearest hit in which / lpos) — what a traced child ray
+//               needs: its own traceRayToLight and the density of the mixture it was sampled from
+template <int MODE>
 __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos) {
+    constexpr bool NEAREST = MODE != LQ_PDF, PDF = MODE != LQ_NEAREST;
     float best_len = IPT_INF, pdf_sum = 0.0f;
     which = IPT_NO_HIT;
     f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -193,7 +200,8 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
                 if (NEAREST) {
                     float len = xlength3(xsub3(hp, o));
                     if (len < best_len || (len == best_len && orig < which)) { best_len = len; which = orig; lpos = hp; }
-                } else {
+                }
+                if (PDF) {
                     f3 dp = mk3(hp.x - o.x, hp.y - o.y, hp.z - o.z);
                     float decay = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
                     float cosinus = -(n.x * dp.x + n.y * dp.y + n.z * dp.z) * rsqrtf(decay);
@@ -205,7 +213,7 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
             f8 n0 = ldg256(&S.light_nodes[node]);
             f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[node]) + 32);
             // entry distances are in units of t; a hit at length L has t = L / |d|
-            float limit = NEAREST ? (best_len / dlen) * 1.0001f + 1e-6f : IPT_INF;
+            float limit = MODE == LQ_NEAREST ? (best_len / dlen) * 1.0001f + 1e-6f : IPT_INF;
             bool h0 = light_box(n0, 0, o, inv, limit), h1 = light_box(n1, 0, o, inv, limit);
             uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
             node = IPT_NO_HIT;
@@ -218,23 +226,28 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
             node = stack[--sp];
         }
     }
-    return NEAREST ? best_len : pdf_sum;
+    return PDF ? pdf_sum : best_len;
 }
 
-// nearest light, scanning in list order with strict `>` (CollectionLighting.cpp:23-34)
-__device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos) {
+// nearest light, scanning in list order with strict `>` (CollectionLighting.cpp:23-34); `lpdf` receives the light part
+// of the mixture density along the same ray, sum_i w_i * DdfFromLight_i::value(d) (lighting.cpp:61-73, ddf.cpp:156-162),
+// which needs exactly the intersections this scan performs (PDF = false: nearest light only)
+template <bool PDF = true>
+__device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& lpdf) {
     bool any = false;
     float best_len = 0.0f;
+    lpdf = 0.0f;
     if (S.n_light_bvh) {
-        light_bvh_query<true>(S, o, d, which, lpos);
+        if (PDF) lpdf = light_bvh_query<LQ_BOTH>(S, o, d, which, lpos);
+        else light_bvh_query<LQ_NEAREST>(S, o, d, which, lpos);
         return which != IPT_NO_HIT;
     }
     if (S.light_inline) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
-            if (i < (int)S.n_lights) trace_one_light(S.lights[i], i, o, d, any, best_len, which, lpos);
+            if (i < (int)S.n_lights) trace_one_light<PDF>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
     } else {
-        for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light(S.lights_g[i], i, o, d, any, best_len, which, lpos);
+        for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light<PDF>(S.lights_g[i], i, o, d, any, best_len, which, lpos, lpdf);
     }
     return any;
 }
@@ -244,6 +257,7 @@ struct Outcome {
     SurfHit surf;
     uint32_t light;
     f3 light_pos;
+    float light_pdf; // light part of the mixture density along the ray (see trace_lights)
 };
 
 // Geometry::traceRay + Lighting::traceRayToLight + the decision of main.cpp:111-128
@@ -253,7 +267,7 @@ __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, Tr
     r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
-    bool lh = trace_lights(S, o, d, r.light, r.light_pos);
+    bool lh = trace_lights(S, o, d, r.light, r.light_pos, r.light_pdf);
     bool sh = r.surf.prim != IPT_NO_HIT;
     r.kind = 0;
     if (lh) {
@@ -278,7 +292,7 @@ __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
     r.surf.prim = IPT_NO_HIT; r.surf.t = IPT_INF; r.surf.tri_pos = IPT_NO_HIT;
-    bool lh = trace_lights(S, o, d, r.light, r.light_pos);
+    bool lh = trace_lights(S, o, d, r.light, r.light_pos, r.light_pdf);
     r.kind = 3;
     if (!lh) return r;
     r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
@@ -292,13 +306,11 @@ __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 
     return r;
 }
 
-// Resolves a ray's weight (see the queue description above): K * sv / (w_light * pdf_light(dir) + w_sdf * sv), the
-// `sdf/mix` multiplier of main.cpp:172-173 with UnionDdf::value (ddf.cpp:156-162) for the one-light mixture.
-__device__ __forceinline__ float resolve_weight(const DevScene& S, float K, float sv, f3 o, bool light_hit, f3 lpos) {
+// Resolves a ray's weight (see the queue description above): K * sv / (sum_i w_i * pdf_light_i(dir) + w_sdf * sv), the
+// `sdf/mix` multiplier of main.cpp:172-173 with UnionDdf::value (ddf.cpp:156-162); `lpdf` comes from trace_lights.
+__device__ __forceinline__ float resolve_weight(const DevScene& S, float K, float sv, float lpdf) {
     if (sv < 0.0f) return K;
-    float lp = 0.0f;
-    if (light_hit) lp = S.lights[0].weight * light_pdf_at(S.lights[0], o, lpos);
-    return K * __fdividef(sv, lp + S.sdf_weight * sv);
+    return K * __fdividef(sv, lpdf + S.sdf_weight * sv);
 }
 
 __device__ __forceinline__ void flush_stat(unsigned long long* stats, int slot, uint32_t v) {
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
             f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
             if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) oc = trace_scene_last<SMALLPT, MESH>(S, o, d, tc);
             else oc = trace_scene<SMALLPT, MESH>(S, o, d, tc);
-            ro.w = resolve_weight(S, ro.w, sv, o, oc.light != IPT_NO_HIT, oc.light_pos);
+            ro.w = resolve_weight(S, ro.w, sv, oc.light_pdf);
             if (!isfinite(ro.w)) { ++n_dropped; oc.kind = 4; } // non-finite multiplier (main.cpp:175): drop this sample
             if (C.flags & 4u)
                 printf("GPU extend d=%u node=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) thr=%.9g kind=%u prim=%u t=%.9g\n", depth,
@@ -491,25 +503,13 @@ __global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : 
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
                 } else {
                     float sv = sdf_value(sdf, w);
-                    if (S.light_inline) {
-                        // one-light scene: k_extend intersects that light for this ray anyway, so the mixture density
-                        // (and with it the weight K*sv/mix) is resolved there; sv == 0 already means weight 0
-                        wgt = thr * albedo * inv_n;
-                        child_sv = sv;
-                        if (!isfinite(sv)) ++n_dropped;
-                        else if (sv == 0.0f && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
-                        else emit = true;
-                    } else {
-                        float mv = mix_value(S, sdf, pos, w, sv);
-                        float mult = __fdividef(sv, mv);
-                        wgt = thr * (mult * albedo) * inv_n;
-                        child_sv = -1.0f;
-                        if (C.flags & 4u)
-                            printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) w=(%.9g %.9g %.9g) sv=%.9g mv=%.9g\n", depth, child, u01(r.x), u01(r.y), u01(r.z), w.x, w.y, w.z, sv, mv);
-                        if (!isfinite(wgt)) ++n_dropped;
-                        else if (wgt == 0.0f && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
-                        else emit = true;
-                    }
+                    // the ray's own light intersection (k_extend, or the fused block below) also yields the light part of
+                    // the mixture density, so the weight K*sv/mix is resolved there; sv == 0 already means weight 0
+                    wgt = thr * albedo * inv_n;
+                    child_sv = sv;
+                    if (!isfinite(sv) || !isfinite(wgt)) ++n_dropped;
+                    else if ((sv == 0.0f || wgt == 0.0f) && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
+                    else emit = true;
                 }
             }
             if (FUSE_LAST) {
@@ -522,8 +522,9 @@ __global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : 
                 if (emit) {
                     ++n_fused;
                     uint32_t li = IPT_NO_HIT;
-                    bool lh = trace_lights(S, pos, w, li, lpos);
-                    float wr = resolve_weight(S, wgt, child_sv, pos, lh, lpos);
+                    float lpdf;
+                    bool lh = trace_lights(S, pos, w, li, lpos, lpdf);
+                    float wr = resolve_weight(S, wgt, child_sv, lpdf);
                     if (!isfinite(wr)) ++n_dropped;
                     else if (lh) {
                         float power = S.light_inline ? S.lights[li].surface_power : S.lights_g[li].surface_power;

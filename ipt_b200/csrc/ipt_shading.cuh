@@ -202,7 +202,7 @@ __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float 
     return dir;
 }
 
-template <bool NEAREST>
+template <int MODE>
 __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos); // ipt_kernels.cuh
 
 // UnionDdf::value over [lights..., sdf] (src/libddf/ddf.cpp:156-162) with the weights of main.cpp:143
@@ -215,7 +215,7 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
     } else if (S.n_light_bvh) {
         uint32_t which;
         f3 lpos;
-        lp = light_bvh_query<false>(S, pos, w, which, lpos);
+        lp = light_bvh_query<0 /* LQ_PDF */>(S, pos, w, which, lpos);
     } else {
         for (uint32_t i = 0; i < S.n_lights; ++i) {
             const DevLight& L = S.lights_g[i];

@@ -222,7 +222,14 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                 bool go = true;
                 if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) { // shadow ray: nothing to do unless a light lies along it
                     lwhich = IPT_NO_HIT;
-                    go = trace_lights(S, o, d, lwhich, lpos);
+                    float lpdf;
+                    if (S.light_inline) {
+                        go = trace_lights<false>(S, o, d, lwhich, lpos, lpdf); // density from lpos when the ray is finalised
+                    } else {
+                        go = trace_lights(S, o, d, lwhich, lpos, lpdf);
+                        ro.w = resolve_weight(S, ro.w, sv, lpdf); // resolved now: no density register lives through the traversal
+                        sv = -1.0f;
+                    }
                 }
                 if (go) {
                     double dd = (double)IPT_INF;
@@ -304,11 +311,18 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
             iprim = tri ? S.n_prims + best_pos : a_prim;
             t = tri ? best_t : a_t;
             bool lh;
+            float lpdf = 0.0f;
             if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) lh = true;
-            else { lwhich = IPT_NO_HIT; lh = trace_lights(S, o, d, lwhich, lpos); }
+            else {
+                lwhich = IPT_NO_HIT;
+                if (S.light_inline) lh = trace_lights<false>(S, o, d, lwhich, lpos, lpdf);
+                else lh = trace_lights(S, o, d, lwhich, lpos, lpdf);
+            }
+            // single inline light: its density follows from the hit position that is kept anyway
+            if (S.light_inline && lh && S.n_lights) lpdf = S.lights[0].weight * light_pdf_at(S.lights[0], o, lpos);
             bool sh = prim != IPT_NO_HIT;
             float K = ro.w;
-            ro.w = resolve_weight(S, ro.w, sv, o, lh, lpos);
+            ro.w = resolve_weight(S, ro.w, sv, lpdf);
             if (C.flags & 4u)
                 printf("GPU mesh extend d=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) K=%.9g sv=%.9g thr=%.9g lh=%d lpos=(%.9g %.9g %.9g) prim=%u t=%.9g\n", depth, o.x, o.y, o.z,
                        d.x, d.y, d.z, K, sv, ro.w, (int)lh, lpos.x, lpos.y, lpos.z, prim, t);
