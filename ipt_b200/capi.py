@@ -251,6 +251,10 @@ class Scene:
         self.handle = _vp()
         check(load().ipt_scene_create(description.ptr, device, C.byref(self.handle)))
 
+    def set_camera(self, camera: Camera):
+        """Replace the camera of the device scene (what Gui::work does after an arrow key, gui.cpp:129-133)."""
+        check(load().ipt_scene_set_camera(self.handle, C.byref(camera)))
+
     def close(self):
         if self.handle:
             load().ipt_scene_destroy(self.handle)

@@ -104,3 +104,36 @@ def test_plane_display_and_save(lib, oracle, tmp_path):
     plane.save_png(tmp_path / "result.png")
     assert np.array_equal(decode_png_gray8((tmp_path / "result.png").read_bytes()), by)
     plane.close(); sc.close()
+
+
+def test_progressive_session_keys_checkpoint_and_resume(lib, oracle, tmp_path):
+    """The reference's interactive loop, headless (ipt_b200/progressive.py): progressive steps, an arrow key that moves the
+    camera and restarts the image (gui.cpp:105-137,152-160), checkpoint + resume equal to the uninterrupted session."""
+    from ipt_b200.progressive import KEY_LEFT, KEY_UP, ProgressiveSession
+
+    kw = dict(scene_name="box", width=64, height=64, passes_per_call=2, seed=5)
+    a = ProgressiveSession(**kw)
+    assert a.step(2) == 4
+    before = a.plane.download()[0].copy()
+    a.key(KEY_LEFT); a.key(KEY_UP)
+    assert a.samples_per_pixel == 0 and a.plane.download()[2].sum() == 0        # resetImage
+    want = oracle.camera_orbit(oracle.camera_orbit([0.0, -3.0, 0.1], list(a.description.desc.camera.direction), 0)[0],
+                               oracle.camera_orbit([0.0, -3.0, 0.1], list(a.description.desc.camera.direction), 0)[1], 3)
+    got = np.array([list(a.camera.position), list(a.camera.direction), list(a.camera.right), list(a.camera.up)], np.float32)
+    assert np.array_equal(bits(got), bits(want))
+    a.step(1)
+    ck = tmp_path / "session.npz"
+    a.checkpoint(ck)
+    a.step(2)
+    s_a, q_a, c_a = a.plane.download()
+    assert a.samples_per_pixel == 6 and (c_a.sum() == 6 * 64 * 64) and not np.allclose(s_a / 6, before / 4, atol=1e-3)  # another view
+    b = ProgressiveSession(checkpoint_path=ck, **kw)                                # a new process would do exactly this
+    assert b.samples_per_pixel == 2 and b.next_pass == a.next_pass - 4
+    b.step(2)
+    s_b, q_b, c_b = b.plane.download()
+    assert np.array_equal(c_a, c_b) and np.allclose(s_a, s_b, rtol=2e-5, atol=1e-7)
+    shown = b.display()
+    assert shown.shape == (64, 64) and shown.max() == 1.0
+    b.save(tmp_path / "result.png")
+    assert np.array_equal(decode_png_gray8((tmp_path / "result.png").read_bytes()), b.plane.save_bytes())
+    a.close(); b.close()
