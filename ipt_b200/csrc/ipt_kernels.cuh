@@ -7,12 +7,13 @@
 //
 // Queues (SoA, one 128-bit load/store per field and thread, coalesced):
 //   ray  : float4 (origin.xyz, K)  float4 (direction.xyz, tag)  float sv                         36 B
-//          one-light scenes: the ray's weight is K * sv / mix(direction) and the mixture density needs the light hit
-//          along the ray, which k_extend computes anyway -> the weight is resolved there (sv < 0: weight = K)
+//          the ray's weight is K * sv / mix(direction) and the mixture density needs the light hits along the ray,
+//          which whoever traces the ray computes anyway -> the weight is resolved there (sv < 0: weight = K)
 //   hit  : float4 (position.xyz, throughput) uint4 (tag, prim, octahedral incoming direction) 32 B
 //   tag  = path slot in the batch | node index within its tree level << slot_bits
 // Live-path compaction: a ray that misses or reaches a light writes nothing; survivors are appended with a
 // warp ballot + one atomicAdd per warp (warp-aggregated stream compaction).
+// The rays of the LAST traced depth of analytic scenes are never queued: k_shade<FUSE_LAST> resolves them itself.
 // All kernels are persistent grid-stride loops over a device-side element count, so no host round trip
 // separates the stages.
 #pragma once
