@@ -131,7 +131,11 @@ enum ipt_render_flags {
     /* Analytic scenes resolve the last traced depth inside the shade kernel that spawns it (the rays of the widest
      * tree level are never queued). This flag keeps them on the queue + k_extend<LAST> path; results are the same up to
      * the order of the float atomics. */
-    IPT_FLAG_NO_FUSED_LAST_LEVEL = 16u
+    IPT_FLAG_NO_FUSED_LAST_LEVEL = 16u,
+    /* Analytic scenes: the shade kernel of every depth traces the children it spawns (no ray queue, no extend launch
+     * after depth 0). This flag puts the children of all but the last shading level back on the ray queue +
+     * k_extend path (IPT_FLAG_NO_FUSED_LAST_LEVEL implies it). Same results up to the order of the float atomics. */
+    IPT_FLAG_NO_FUSED_TRACE = 32u
 };
 
 typedef struct ipt_render_params {

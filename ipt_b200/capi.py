@@ -13,7 +13,7 @@ import numpy as np
 IPT_MAX_DEPTH = 16
 IPT_NO_HIT = 0xFFFFFFFF
 PLANE_GRID, PLANE_GUI, PLANE_LINEAR = 0, 1, 2
-FLAG_TIME_KERNELS, FLAG_KEEP_ZERO_WEIGHT, FLAG_DEBUG_PRINT, FLAG_RESOLVE_LAST_LEVEL, FLAG_NO_FUSED_LAST_LEVEL = 1, 2, 4, 8, 16
+FLAG_TIME_KERNELS, FLAG_KEEP_ZERO_WEIGHT, FLAG_DEBUG_PRINT, FLAG_RESOLVE_LAST_LEVEL, FLAG_NO_FUSED_LAST_LEVEL, FLAG_NO_FUSED_TRACE = 1, 2, 4, 8, 16, 32
 STATUS = {0: "IPT_OK", 1: "IPT_ERR_INVALID", 2: "IPT_ERR_CUDA", 3: "IPT_ERR_NO_DEVICE", 4: "IPT_ERR_UNSUPPORTED", 5: "IPT_ERR_OVERFLOW"}
 IPT_ERR_INVALID = 1
 IPT_ERR_NO_DEVICE = 3

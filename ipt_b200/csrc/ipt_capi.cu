@@ -57,8 +57,11 @@ struct Workspace {
     float* ray_x = nullptr;
     float4* hit_a = nullptr;
     uint4* hit_b = nullptr;
+    float4* hit_a2 = nullptr; // second hit set, only when the shade kernels trace their own children
+    uint4* hit_b2 = nullptr;
     float* pathval = nullptr;
     size_t ray_cap = 0, hit_cap = 0, path_cap = 0;
+    bool two_hit_sets = false;
 };
 
 // grow-only device scratch of the output stage (ipt_output.cuh): cudaMalloc/cudaFree per call would cost more than the
@@ -104,7 +107,7 @@ struct ipt_scene {
     float* pinned = nullptr;         // staging for ipt_render_host
     size_t pinned_bytes = 0;
     int grid_mesh = 0, grid_mesh_last = 0;
-    int grid_generate = 0, grid_extend = 0, grid_extend_last = 0, grid_shade = 0, grid_shade_fused = 0, grid_accumulate = 0;
+    int grid_generate = 0, grid_extend = 0, grid_extend_last = 0, grid_shade = 0, grid_shade_fused = 0, grid_shade_next = 0, grid_accumulate = 0;
     OutputScratch out;
 };
 
@@ -521,8 +524,9 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
 
     size_t sm = stack_smem(s);
     s->grid_generate = occupancy_grid(k_generate, s->sm_count, 0);
-    s->grid_shade = occupancy_grid(k_shade<false, false>, s->sm_count, 0);
-    s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<true, true>, s->sm_count, 0) : occupancy_grid(k_shade<true, false>, s->sm_count, 0);
+    s->grid_shade = occupancy_grid(k_shade<FUSE_NONE, false>, s->sm_count, 0);
+    s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0) : occupancy_grid(k_shade<FUSE_LAST, false>, s->sm_count, 0);
+    s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0) : occupancy_grid(k_shade<FUSE_NEXT, false>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
         s->grid_mesh = occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
@@ -538,7 +542,8 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
 }
 
 static void free_workspace(Workspace& w) {
-    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.ray_x); cudaFree(w.hit_a); cudaFree(w.hit_b); cudaFree(w.pathval);
+    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.ray_x); cudaFree(w.hit_a); cudaFree(w.hit_b); cudaFree(w.hit_a2); cudaFree(w.hit_b2);
+    cudaFree(w.pathval);
     w = Workspace();
 }
 
@@ -886,9 +891,9 @@ void ipt_render_params_default(ipt_render_params* p) {
     p->plane_mode = IPT_PLANE_GRID;
 }
 
-static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t path_cap) {
+static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t path_cap, bool two_hit_sets) {
     Workspace& w = s->ws;
-    if (w.ray_cap >= ray_cap && w.hit_cap >= hit_cap && w.path_cap >= path_cap) return IPT_OK;
+    if (w.ray_cap >= ray_cap && w.hit_cap >= hit_cap && w.path_cap >= path_cap && (w.two_hit_sets || !two_hit_sets)) return IPT_OK;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     free_workspace(w);
     CUDA_TRY(cudaMalloc((void**)&w.ray_o, 16 * ray_cap));
@@ -896,8 +901,12 @@ static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t
     CUDA_TRY(cudaMalloc((void**)&w.ray_x, 4 * ray_cap));
     CUDA_TRY(cudaMalloc((void**)&w.hit_a, 16 * std::max<size_t>(hit_cap, 1)));
     CUDA_TRY(cudaMalloc((void**)&w.hit_b, 16 * std::max<size_t>(hit_cap, 1)));
+    if (two_hit_sets) {
+        CUDA_TRY(cudaMalloc((void**)&w.hit_a2, 16 * std::max<size_t>(hit_cap, 1)));
+        CUDA_TRY(cudaMalloc((void**)&w.hit_b2, 16 * std::max<size_t>(hit_cap, 1)));
+    }
     CUDA_TRY(cudaMalloc((void**)&w.pathval, 4 * path_cap));
-    w.ray_cap = ray_cap; w.hit_cap = hit_cap; w.path_cap = path_cap;
+    w.ray_cap = ray_cap; w.hit_cap = hit_cap; w.path_cap = path_cap; w.two_hit_sets = two_hit_sets;
     return IPT_OK;
 }
 
@@ -915,7 +924,9 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     if (p->plane_mode > IPT_PLANE_LINEAR) return fail(IPT_ERR_INVALID, "unknown plane mode");
     CUDA_TRY(cudaSetDevice(s->device));
 
+    // analytic scenes: the shade kernels trace the children they spawn (FUSE_NEXT / FUSE_LAST in ipt_kernels.cuh)
     const bool fuse_last = !s->mesh && !(p->flags & (IPT_FLAG_DEBUG_PRINT | IPT_FLAG_RESOLVE_LAST_LEVEL | IPT_FLAG_NO_FUSED_LAST_LEVEL));
+    const bool fuse_next = fuse_last && !(p->flags & IPT_FLAG_NO_FUSED_TRACE);
     // widest tree level among traced depths -> bits for the node index inside the ray tag
     uint64_t width_at[IPT_MAX_DEPTH];
     uint64_t w = 1, max_ray_w = 1, max_hit_w = 1, max_queued_w = 1;
@@ -924,7 +935,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
         max_ray_w = std::max(max_ray_w, w);
         // with the fused last level the rays of the last traced depth (> 0) are never queued
         bool is_last = d + 1 == p->depth_max || p->schedule[d] == 0;
-        if (!(fuse_last && is_last && d > 0)) max_queued_w = std::max(max_queued_w, w);
+        if (!(fuse_last && is_last && d > 0) && !(fuse_next && d > 0)) max_queued_w = std::max(max_queued_w, w);
         if (d + 1 < p->depth_max) max_hit_w = std::max(max_hit_w, w);
         w *= p->schedule[d];
         if (w > (1ull << 31)) return fail(IPT_ERR_UNSUPPORTED, "split schedule too wide (more than 2^31 nodes per tree level)");
@@ -941,17 +952,20 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     // for narrow schedules such as depth 8 with one child per hit, whose deeper levels would otherwise be tiny launches)
     // (with the fused last level the widest level is not queued: 2^27 / widest queued level, i.e. 2^20 paths at 16/8/4/2)
     uint64_t batch_rays = max_queued_w < max_ray_w ? (1ull << 27) : (1ull << 28);
-    uint64_t batch = p->batch_paths ? p->batch_paths : std::min<uint64_t>(1ull << 23, std::max<uint64_t>(1ull << 16, batch_rays / max_queued_w));
+    uint64_t batch_w = fuse_next ? max_hit_w : max_queued_w; // fused: what is queued are the hits
+    uint64_t batch = p->batch_paths ? p->batch_paths : std::min<uint64_t>(1ull << 23, std::max<uint64_t>(1ull << 16, batch_rays / batch_w));
     batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
     const uint64_t budget = 24ull << 30; // bytes of queue memory
-    while (batch > 1024 && batch * (max_queued_w * 36 + max_hit_w * 32) > budget) batch >>= 1;
+    while (batch > 1024 && batch * (max_queued_w * 36 + max_hit_w * 32 * (fuse_next ? 2 : 1)) > budget) batch >>= 1;
     batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(total_paths, 1)));
-    int rc = ensure_workspace(s, batch * max_queued_w, batch * max_hit_w, batch);
+    int rc = ensure_workspace(s, batch * max_queued_w, batch * max_hit_w, batch, fuse_next);
     if (rc) return rc;
 
     RenderCtx C;
     std::memset(&C, 0, sizeof C);
-    C.ray_o = s->ws.ray_o; C.ray_d = s->ws.ray_d; C.ray_x = s->ws.ray_x; C.hit_a = s->ws.hit_a; C.hit_b = s->ws.hit_b; C.pathval = s->ws.pathval;
+    C.ray_o = s->ws.ray_o; C.ray_d = s->ws.ray_d; C.ray_x = s->ws.ray_x; C.pathval = s->ws.pathval;
+    C.hit_a[0] = s->ws.hit_a; C.hit_b[0] = s->ws.hit_b;
+    C.hit_a[1] = fuse_next ? s->ws.hit_a2 : s->ws.hit_a; C.hit_b[1] = fuse_next ? s->ws.hit_b2 : s->ws.hit_b;
     C.cnt = s->d_cnt; C.fetch = s->d_cnt + (2 * IPT_MAX_DEPTH + 2); C.stats = s->d_stats;
     C.sum = plane->sum; C.sumsq = plane->sumsq; C.count = plane->count;
     C.width = p->width; C.height = p->height;
@@ -993,6 +1007,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     } while (0)
         int gg = std::min<int>(s->grid_generate, (int)((C.batch + IPT_BLOCK - 1) / IPT_BLOCK));
         TIMED(0, (k_generate<<<gg, IPT_BLOCK, 0, s->stream>>>(s->dev, C)));
+        bool traced = false; // the shade kernel of the previous depth has already traced the rays of this depth
         for (uint32_t d = 0; d < p->depth_max; ++d) {
             if (width_at[d] == 0) break;
             bool last = (d + 1 == p->depth_max) || p->schedule[d] == 0;
@@ -1008,31 +1023,41 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 }
                 TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
                 int gs2 = std::max(1, std::min(s->grid_shade, cap_blocks));
-                TIMED(2, (k_shade<false, false><<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                TIMED(2, (k_shade<FUSE_NONE, false><<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 continue;
             }
-            if (last) {
-                int g = std::max(1, std::min(s->grid_extend_last, cap_blocks));
+            if (!traced) { // the rays of this depth wait in the ray queue (depth 0, or an unfused run)
+                if (last) {
+                    int g = std::max(1, std::min(s->grid_extend_last, cap_blocks));
 #define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
+                    DISPATCH_SM(s, CALL);
+#undef CALL
+                    break;
+                }
+                int g = std::max(1, std::min(s->grid_extend, cap_blocks));
+#define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
                 DISPATCH_SM(s, CALL);
 #undef CALL
-                break;
             }
-            int g = std::max(1, std::min(s->grid_extend, cap_blocks));
-#define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
-            DISPATCH_SM(s, CALL);
-#undef CALL
+            traced = false;
             // the children of this level are the last traced depth: resolve them inside the shade kernel (no queue, no
             // k_extend<LAST> launch); analytic scenes only, and not when a flag asks for the unfused behaviour
             bool child_last = width_at[d + 1] != 0 && ((d + 2 == p->depth_max) || p->schedule[d + 1] == 0);
             if (child_last && fuse_last) {
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
-                if (s->smallpt) TIMED(2, (k_shade<true, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else TIMED(2, (k_shade<true, false><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_LAST, false><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 break;
             }
+            if (fuse_next && width_at[d + 1] != 0) {
+                int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
+                if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_NEXT, false><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                traced = true; // the rays of depth d+1 are traced by this launch: no k_extend for them
+                continue;
+            }
             int gs = std::max(1, std::min(s->grid_shade, cap_blocks));
-            TIMED(2, (k_shade<false, false><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+            TIMED(2, (k_shade<FUSE_NONE, false><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
         }
         TIMED(3, (k_accumulate<<<std::max(1, gg), IPT_BLOCK, 0, s->stream>>>(C)));
 #undef TIMED

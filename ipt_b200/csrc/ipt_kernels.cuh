@@ -24,6 +24,9 @@
 #ifndef IPT_SHADE_FUSED_MIN_BLOCKS
 #define IPT_SHADE_FUSED_MIN_BLOCKS 3 // 80 registers, 156 B of spills: still 4 % faster than 2 blocks (profiles/tuning_r01.md)
 #endif
+#ifndef IPT_SHADE_NEXT_MIN_BLOCKS
+#define IPT_SHADE_NEXT_MIN_BLOCKS 3
+#endif
 #ifndef IPT_EXTEND_MIN_BLOCKS
 #define IPT_EXTEND_MIN_BLOCKS 3
 #endif
@@ -44,8 +47,8 @@ struct RenderCtx {
     float4* ray_o;
     float4* ray_d;
     float* ray_x;              // sdf value of the sampled direction (weight resolution is deferred to k_extend), or -1
-    float4* hit_a;
-    uint4* hit_b;
+    float4* hit_a[2];          // hits of depth d live in set d & 1: the fused shade kernel reads one set while it fills the other
+    uint4* hit_b[2];           // (the two sets alias where extend and shade are separate launches)
     float* pathval;
     uint32_t* cnt;             // [2*d] rays at depth d, [2*d+1] surface hits at depth d
     uint32_t* fetch;           // [d] next unfetched ray of depth d (persistent mesh kernel)
@@ -73,24 +76,24 @@ __device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2])
 // the incoming direction, which only the glossy lobe (reflect(d, n)) needs. The parent ray record cannot be re-read
 // at shading time: the shade kernel is already overwriting the ray queue with the next depth.
 __device__ __forceinline__ float2 oct_encode(f3 d) {
-    float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
-    float px = d.x * inv, py = d.y * inv;
+    float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(fabsf(d.x), fabsf(d.y)), fabsf(d.z)));
+    float px = pmul(d.x, inv), py = pmul(d.y, inv);
     if (d.z < 0.0f) {
-        float tx = (1.0f - fabsf(py)) * copysignf(1.0f, px);
-        py = (1.0f - fabsf(px)) * copysignf(1.0f, py);
+        float tx = copysignf(__fsub_rn(1.0f, fabsf(py)), px);
+        py = copysignf(__fsub_rn(1.0f, fabsf(px)), py);
         px = tx;
     }
     return make_float2(px, py);
 }
 __device__ __forceinline__ f3 oct_decode(float ex, float ey) {
-    float z = 1.0f - fabsf(ex) - fabsf(ey);
+    float z = __fsub_rn(__fsub_rn(1.0f, fabsf(ex)), fabsf(ey));
     float x = ex, y = ey;
     if (z < 0.0f) {
-        x = (1.0f - fabsf(ey)) * copysignf(1.0f, ex);
-        y = (1.0f - fabsf(ex)) * copysignf(1.0f, ey);
+        x = copysignf(__fsub_rn(1.0f, fabsf(ey)), ex);
+        y = copysignf(__fsub_rn(1.0f, fabsf(ex)), ey);
     }
-    float inv = rsqrtf(x * x + y * y + z * z);
-    return mk3(x * inv, y * inv, z * inv);
+    float inv = rsqrtf(dot3(mk3(x, y, z), mk3(x, y, z)));
+    return mk3(pmul(x, inv), pmul(y, inv), pmul(z, inv));
 }
 
 // slot -> loop pixel and pass (render_sample's iy/ix loops, main.cpp:189-190)
@@ -161,7 +164,7 @@ __device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f
         which = i;
         lpos = e.position;
     }
-    if (PDF) lpdf += L.weight * light_pdf_at(L, o, e.position);
+    if (PDF) lpdf = pfma(L.weight, light_pdf_at(L, o, e.position), lpdf);
 }
 // conservative ray/box test for the light LBVH (see slab() in ipt_trace.cuh); limit = farthest useful entry distance
 __device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, float limit) {
@@ -203,10 +206,10 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
                     if (len < best_len || (len == best_len && orig < which)) { best_len = len; which = orig; lpos = hp; }
                 }
                 if (PDF) {
-                    f3 dp = mk3(hp.x - o.x, hp.y - o.y, hp.z - o.z);
-                    float decay = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
-                    float cosinus = -(n.x * dp.x + n.y * dp.y + n.z * dp.z) * rsqrtf(decay);
-                    if (cosinus >= 0.0f) pdf_sum += r1.v[7] * __fdividef(decay, cosinus * r1.v[6]);
+                    f3 dp = mk3(__fsub_rn(hp.x, o.x), __fsub_rn(hp.y, o.y), __fsub_rn(hp.z, o.z));
+                    float decay = dot3(dp, dp);
+                    float cosinus = pmul(-dot3(n, dp), rsqrtf(decay));
+                    if (cosinus >= 0.0f) pdf_sum = pfma(r1.v[7], __fdividef(decay, pmul(cosinus, r1.v[6])), pdf_sum);
                 }
             }
             node = IPT_NO_HIT;
@@ -311,7 +314,7 @@ __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 
 // `sdf/mix` multiplier of main.cpp:172-173 with UnionDdf::value (ddf.cpp:156-162); `lpdf` comes from trace_lights.
 __device__ __forceinline__ float resolve_weight(const DevScene& S, float K, float sv, float lpdf) {
     if (sv < 0.0f) return K;
-    return K * __fdividef(sv, lpdf + S.sdf_weight * sv);
+    return pmul(K, __fdividef(sv, pfma(S.sdf_weight, sv, lpdf)));
 }
 
 __device__ __forceinline__ void flush_stat(unsigned long long* stats, int slot, uint32_t v) {
@@ -373,8 +376,8 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
                     f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), oc.surf.t);
                     uint32_t iprim = oc.surf.tri_pos != IPT_NO_HIT ? S.n_prims + oc.surf.tri_pos : oc.surf.prim;
                     float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
-                    C.hit_a[j] = make_float4(p.x, p.y, p.z, ro.w);
-                    C.hit_b[j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+                    C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, ro.w);
+                    C.hit_b[depth & 1][j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
                 }
             }
         }
@@ -437,13 +440,65 @@ __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCt
     } else ++n_surface;
 }
 
+struct ExtendCounters {
+    uint32_t surface, light, miss, dropped;
+};
+// The body of k_extend<.., LAST = false> for one parked child ray of depth `depth` (entry k of the warp's queue; all 32
+// lanes call this, `valid` masks the drain): trace_scene, weight resolution, emission, and the warp-aggregated append
+// of the surface hits to the hit set of `depth`.
+template <bool SMALLPT>
+__device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, bool valid, uint32_t depth,
+                                              TraceCounters& tc, ExtendCounters& ec) {
+    const uint32_t lane = threadIdx.x & 31;
+    bool emit = false;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
+    float wr = 0.0f;
+    uint32_t ctag = 0;
+    Outcome oc;
+    if (valid) {
+        o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
+        d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
+        ctag = __float_as_uint(dq[8 * IPT_PARK + k]);
+        oc = trace_scene<SMALLPT, false>(S, o, d, tc);
+        wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
+        if (!isfinite(wr)) ++ec.dropped; // non-finite multiplier (main.cpp:175): drop this sample
+        else if (oc.kind == 2) {
+            ++ec.light;
+            float power = S.light_inline ? S.lights[oc.light].surface_power : S.lights_g[oc.light].surface_power;
+            if (!isfinite(power)) power = 1.0f; // main.cpp:123 point-light hack
+            atomicAdd(&C.pathval[ctag & C.slot_mask], wr * power);
+        } else if (oc.kind == 1) {
+            ++ec.surface;
+            emit = true;
+        } else ++ec.miss;
+    }
+    uint32_t ballot = __ballot_sync(0xffffffffu, emit);
+    if (ballot) {
+        uint32_t basepos = 0;
+        if (lane == 0) basepos = atomicAdd(&C.cnt[2 * depth + 1], (uint32_t)__popc(ballot));
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        if (emit) {
+            uint32_t j = basepos + __popc(ballot & ((1u << lane) - 1u));
+            f3 p = xpoint(o, d, oc.surf.t);
+            float2 oct = oct_encode(d);
+            C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, wr);
+            C.hit_b[depth & 1][j] = make_uint4(ctag, oc.surf.prim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+        }
+    }
+}
+
 // K3 shade: one thread per surface hit; spawns schedule[depth] children from the 1:1 mixture of the light DDF
-// and the surface DDF (main.cpp:142-177) and appends the survivors to the ray queue of depth+1.
-// FUSE_LAST (analytic scenes, children are the last traced depth): the children are "shadow rays" (see
-// trace_scene_last), so instead of being queued for k_extend<LAST> they are resolved right here — same functions, same
-// operands, same counters; the widest level of the tree never touches memory.
-template <bool FUSE_LAST, bool SMALLPT>
-__global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : IPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
+// and the surface DDF (main.cpp:142-177).
+//   FUSE_NONE  the survivors are appended to the ray queue of depth+1 (mesh scenes: k_extend_mesh traces them).
+//   FUSE_NEXT  (analytic scenes) the children are traced HERE: each one is parked in a per-warp shared-memory queue and
+//              whenever 32 are waiting the warp runs the body of k_extend for them (extend_parked) — full warps, no ray
+//              record written or read, no k_extend launch; surface hits go to the other hit set (depth+1).
+//   FUSE_LAST  (analytic scenes, children are the last traced depth) the children are "shadow rays" (trace_scene_last):
+//              light test at once, and only the rays that reach a light are parked for the occlusion test.
+// Same functions, same operands, same counters as the separate kernels.
+enum ShadeFusion { FUSE_NONE = 0, FUSE_NEXT = 1, FUSE_LAST = 2 };
+template <int FUSE, bool SMALLPT>
+__global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : FUSE == FUSE_NEXT ? IPT_SHADE_NEXT_MIN_BLOCKS : IPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth + 1];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -452,9 +507,10 @@ __global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : 
     const float inv_n = 1.0f / (float)n_children;
     uint32_t n_failed = 0, n_pruned = 0, n_dropped = 0;
     uint32_t n_fused = 0, n_light = 0, n_surface = 0;
+    ExtendCounters ec{0, 0, 0, 0};
     TraceCounters tc{0, 0};
-    __shared__ float dq_all[FUSE_LAST ? (256 / 32) * 11 * IPT_PARK : 1];
-    float* dq = dq_all + (FUSE_LAST ? (threadIdx.x >> 5) * 11 * IPT_PARK : 0); // this warp's parked occlusion tests
+    __shared__ float dq_all[FUSE != FUSE_NONE ? (256 / 32) * 11 * IPT_PARK : 1];
+    float* dq = dq_all + (FUSE != FUSE_NONE ? (threadIdx.x >> 5) * 11 * IPT_PARK : 0); // this warp's parked rays
     uint32_t qn = 0;                                                            // warp-uniform
     uint32_t* out_count = &C.cnt[2 * (depth + 1)];
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
@@ -467,8 +523,8 @@ __global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : 
         Basis bn, bl;
         float albedo = 1.0f;
         if (active) {
-            float4 a = C.hit_a[i];
-            uint4 b = C.hit_b[i];
+            float4 a = C.hit_a[depth & 1][i];
+            uint4 b = C.hit_b[depth & 1][i];
             pos = mk3(a.x, a.y, a.z);
             thr = a.w;
             tag = b.x;
@@ -506,14 +562,35 @@ __global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : 
                     float sv = sdf_value(sdf, w);
                     // the ray's own light intersection (k_extend, or the fused block below) also yields the light part of
                     // the mixture density, so the weight K*sv/mix is resolved there; sv == 0 already means weight 0
-                    wgt = thr * albedo * inv_n;
+                    wgt = pmul(pmul(thr, albedo), inv_n);
                     child_sv = sv;
                     if (!isfinite(sv) || !isfinite(wgt)) ++n_dropped;
                     else if ((sv == 0.0f || wgt == 0.0f) && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
                     else emit = true;
                 }
             }
-            if (FUSE_LAST) {
+            if (FUSE == FUSE_NEXT) {
+                uint32_t pb = __ballot_sync(0xffffffffu, emit);
+                if (pb) {
+                    if (emit) {
+                        ++n_fused;
+                        uint32_t k = qn + __popc(pb & ((1u << lane) - 1u));
+                        uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
+                        dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
+                        dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
+                        dq[6 * IPT_PARK + k] = wgt; dq[7 * IPT_PARK + k] = child_sv; dq[8 * IPT_PARK + k] = __uint_as_float(ctag);
+                    }
+                    qn += __popc(pb);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        qn -= 32;
+                        extend_parked<SMALLPT>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
+                        __syncwarp();
+                    }
+                }
+                continue;
+            }
+            if (FUSE == FUSE_LAST) {
                 // the body of k_extend<LAST> for this ray, in two steps: the light test now; the occlusion test of the
                 // rays that did reach a light (about a third) is parked in a per-warp shared-memory queue and run 32 at a
                 // time, so the geometry intersection is issued for full warps instead of for the third of the lanes
@@ -569,13 +646,16 @@ __global__ void __launch_bounds__(256, FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : 
             }
         }
     }
-    if (FUSE_LAST && lane < qn) resolve_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface); // drain
+    if (FUSE == FUSE_LAST && lane < qn) resolve_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface); // drain
+    if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
+    n_light += ec.light; n_surface += ec.surface; n_dropped += ec.dropped;
     flush_stat(C.stats, ST_FAILED, n_failed);
     flush_stat(C.stats, ST_PRUNED, n_pruned);
     flush_stat(C.stats, ST_DROPPED, n_dropped);
-    if (FUSE_LAST) {
+    if (FUSE != FUSE_NONE) {
         flush_stat(C.stats, ST_LIGHT, n_light);
         flush_stat(C.stats, ST_SURFACE, n_surface);
+        flush_stat(C.stats, ST_MISS, ec.miss);
         // rays of depth+1 that were traced without being queued: k_accumulate folds cnt[] into the per-depth ray counts
         for (int off = 16; off > 0; off >>= 1) n_fused += __shfl_down_sync(0xffffffffu, n_fused, off);
         if (lane == 0 && n_fused) {

@@ -26,6 +26,13 @@ __device__ __forceinline__ float frcp(float x) {
     return r;
 }
 
+// The sampling code spells out its multiply-adds (__fmaf_rn / __fmul_rn / ...): left to the compiler, the contraction
+// of a*b + c into an FMA depends on the surrounding code, so the SAME source gave directions differing in the last bit
+// between the instantiations of k_shade — harmless statistically, but then "fused" and "queued" runs could not be
+// compared ray for ray.
+__device__ __forceinline__ float pmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float pfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
 struct Basis { // columns of RotateDdf::transformation; c2 == the axis rotated to
     f3 c0, c1, c2;
 };
@@ -34,25 +41,26 @@ struct Basis { // columns of RotateDdf::transformation; c2 == the axis rotated t
 __device__ __forceinline__ Basis make_basis(f3 to) {
     float c = to.z;
     float axx = -to.y, axy = to.x; // cross((0,0,1), to) = (-to.y, to.x, 0)
-    float len2 = axx * axx + axy * axy;
+    float len2 = pfma(axy, axy, pmul(axx, axx));
     float s = fsqrt(len2);
     float ax, ay;
     if (s < 1e-6f) { ax = 1.0f; ay = 0.0f; } // ddf_detail.h:77-78 degenerate axis -> (1,0,0)
-    else { float inv = frcp(s); ax = axx * inv; ay = axy * inv; }
+    else { float inv = frcp(s); ax = pmul(axx, inv); ay = pmul(axy, inv); }
     // with the degenerate axis the angle is still acos(c): c = +-1, sin = sqrt(1-c*c)
-    float sn = fsqrt(fmaxf(0.0f, 1.0f - c * c));
-    float tx = (1.0f - c) * ax, ty = (1.0f - c) * ay;
+    float sn = fsqrt(fmaxf(0.0f, pfma(-c, c, 1.0f)));
+    float omc = __fsub_rn(1.0f, c);
+    float tx = pmul(omc, ax), ty = pmul(omc, ay);
     Basis b;
-    b.c0 = mk3(c + tx * ax, tx * ay, -sn * ay);
-    b.c1 = mk3(ty * ax, c + ty * ay, sn * ax);
-    b.c2 = mk3(sn * ay, -sn * ax, c);
+    b.c0 = mk3(pfma(tx, ax, c), pmul(tx, ay), pmul(-sn, ay));
+    b.c1 = mk3(pmul(ty, ax), pfma(ty, ay, c), pmul(sn, ax));
+    b.c2 = mk3(pmul(sn, ay), pmul(-sn, ax), c);
     return b;
 }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return pfma(a.z, b.z, pfma(a.y, b.y, pmul(a.x, b.x))); }
 __device__ __forceinline__ f3 rotate(const Basis& b, f3 x) {
-    return mk3(b.c0.x * x.x + b.c1.x * x.y + b.c2.x * x.z, b.c0.y * x.x + b.c1.y * x.y + b.c2.y * x.z,
-               b.c0.z * x.x + b.c1.z * x.y + b.c2.z * x.z);
+    return mk3(pfma(b.c2.x, x.z, pfma(b.c1.x, x.y, pmul(b.c0.x, x.x))), pfma(b.c2.y, x.z, pfma(b.c1.y, x.y, pmul(b.c0.y, x.x))),
+               pfma(b.c2.z, x.z, pfma(b.c1.z, x.y, pmul(b.c0.z, x.x))));
 }
-__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 // Base DDFs in their own frame. kind: 0 Spherical (ddf.cpp:58-72), 1 UpperHalf (:74-89), 2 Cosine (:91-108),
 // >=3 PowerCosine(kind) (extension, oracle/ref_driver.cpp).
@@ -100,8 +108,8 @@ struct Sdf {
     float lobe_norm;  // (n + 1) / (2 pi)
 };
 __device__ __forceinline__ f3 reflect3(f3 I, f3 N) { // glm::reflect: I - N*dot(N,I)*2
-    float k = 2.0f * dot3(N, I);
-    return mk3(I.x - N.x * k, I.y - N.y * k, I.z - N.z * k);
+    float k = pmul(2.0f, dot3(N, I));
+    return mk3(pfma(-N.x, k, I.x), pfma(-N.y, k, I.y), pfma(-N.z, k, I.z));
 }
 __device__ __forceinline__ Sdf make_sdf(const DevMaterial& m, f3 normal, f3 dir_in) {
     Sdf s;
@@ -120,8 +128,8 @@ __device__ __forceinline__ Sdf make_sdf(const DevMaterial& m, f3 normal, f3 dir_
 __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
     float cn = dot3(s.normal, w);
     float zr = dot3(s.refl, w);
-    float lobe = zr > 0.0f ? exp2f(s.exponent * log2f(zr)) : 0.0f;
-    float v = s.wd * (cn * (1.0f / IPT_PI_F)) + s.ws * (s.lobe_norm * lobe);
+    float lobe = zr > 0.0f ? exp2f(pmul(s.exponent, log2f(zr))) : 0.0f;
+    float v = pfma(s.ws, pmul(s.lobe_norm, lobe), pmul(s.wd, pmul(cn, 1.0f / IPT_PI_F)));
     return cn < 0.0f ? 0.0f : v;
 }
 // zero vector == failed sample. ul is the lobe-selection draw (ROLE_LOBE in the oracle).
@@ -129,11 +137,11 @@ __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
 __device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, const Basis& bl, float u1, float u2, float ul) {
     bool lobe = !(ul < s.wd);               // never for Lambert (wd = 1 > ul)
     float e = lobe ? s.inv_np1 : 0.5f;      // cos(alpha) = u1^(1/(n+1)); sqrt(u1) for the cosine DDF (ddf.cpp:94)
-    float zc = exp2f(__log2f(u1) * e);      // u1 = 0 -> 0
-    float r = fsqrt(fmaxf(0.0f, 1.0f - zc * zc));
-    float a = (2.0f * u2 - 1.0f) * IPT_PI_F; // see base_sample
+    float zc = exp2f(pmul(__log2f(u1), e)); // u1 = 0 -> 0
+    float r = fsqrt(fmaxf(0.0f, pfma(-zc, zc, 1.0f)));
+    float a = pmul(pfma(2.0f, u2, -1.0f), IPT_PI_F); // see base_sample
     float sp = -__sinf(a), cp = -__cosf(a);
-    f3 x = mk3(r * cp, r * sp, zc);
+    f3 x = mk3(pmul(r, cp), pmul(r, sp), zc);
     Basis b;
     b.c0 = lobe ? bl.c0 : bn.c0;
     b.c1 = lobe ? bl.c1 : bn.c1;
@@ -150,9 +158,9 @@ __device__ __forceinline__ float light_pdf(const DevLight& L, f3 pos, f3 w) {
     f3 dp = mk3(h.position.x - pos.x, h.position.y - pos.y, h.position.z - pos.z);
     float decay = dot3(dp, dp);
     float inv = rsqrtf(decay);
-    float cosinus = -(h.normal.x * dp.x + h.normal.y * dp.y + h.normal.z * dp.z) * inv;
+    float cosinus = pmul(-dot3(h.normal, dp), inv);
     if (cosinus < 0.0f) return 0.0f;
-    return __fdividef(decay, cosinus * L.area);
+    return __fdividef(decay, pmul(cosinus, L.area));
 }
 
 // The same density from an already known light hit (its position on light L along the ray from `pos`): what
@@ -165,38 +173,39 @@ __device__ __forceinline__ float light_pdf_at(const DevLight& L, f3 pos, f3 hit)
     if (L.kind <= IPT_LIGHT_AREA_TRIANGLE) n = mk3(L.nx, L.ny, L.nz);
     else {
         float ir = 1.0f / L.radius;
-        n = mk3((hit.x - L.px) * ir, (hit.y - L.py) * ir, (hit.z - L.pz) * ir);
+        n = mk3(pmul(__fsub_rn(hit.x, L.px), ir), pmul(__fsub_rn(hit.y, L.py), ir), pmul(__fsub_rn(hit.z, L.pz), ir));
         if (L.kind == IPT_LIGHT_SPHERE_INVERTED) n = neg3(n);
     }
-    float cosinus = -dot3(n, dp) * rsqrtf(decay);
+    float cosinus = pmul(-dot3(n, dp), rsqrtf(decay));
     if (cosinus < 0.0f) return 0.0f;
-    return __fdividef(decay, cosinus * L.area);
+    return __fdividef(decay, pmul(cosinus, L.area));
 }
 
 // DdfFromLight::sample (src/lighting/lighting.cpp:50-59) over Light::sample (lighting.cpp:93-104, 172-207)
 __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float u1, float u2) {
     f3 p, n;
     if (L.kind <= IPT_LIGHT_AREA_TRIANGLE) {
-        float v2 = L.kind == IPT_LIGHT_AREA_TRIANGLE ? u2 * (1.0f - u1) : u2;
-        p = mk3(L.xax * u1 + L.yax * v2 + L.px, L.xay * u1 + L.yay * v2 + L.py, L.xaz * u1 + L.yaz * v2 + L.pz);
+        float v2 = L.kind == IPT_LIGHT_AREA_TRIANGLE ? pmul(u2, __fsub_rn(1.0f, u1)) : u2;
+        p = mk3(__fadd_rn(pfma(L.yax, v2, pmul(L.xax, u1)), L.px), __fadd_rn(pfma(L.yay, v2, pmul(L.xay, u1)), L.py),
+                __fadd_rn(pfma(L.yaz, v2, pmul(L.xaz, u1)), L.pz));
         n = mk3(L.nx, L.ny, L.nz);
     } else {
-        float z = u1 * 2.0f - 1.0f;
-        float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+        float z = pfma(u1, 2.0f, -1.0f);
+        float r = sqrtf(fmaxf(0.0f, pfma(-z, z, 1.0f)));
         float sp, cp;
-        sincospif(2.0f * u2, &sp, &cp);
-        f3 unit = mk3(r * cp, r * sp, z);
+        sincospif(pmul(2.0f, u2), &sp, &cp);
+        f3 unit = mk3(pmul(r, cp), pmul(r, sp), z);
         if (L.kind == IPT_LIGHT_POINT) {
             p = mk3(L.px, L.py, L.pz);
             n = unit;
         } else {
-            p = mk3(unit.x * L.radius + L.px, unit.y * L.radius + L.py, unit.z * L.radius + L.pz);
+            p = mk3(pfma(unit.x, L.radius, L.px), pfma(unit.y, L.radius, L.py), pfma(unit.z, L.radius, L.pz));
             n = L.kind == IPT_LIGHT_SPHERE_INVERTED ? neg3(unit) : unit;
         }
     }
-    f3 dp = mk3(p.x - pos.x, p.y - pos.y, p.z - pos.z);
+    f3 dp = mk3(__fsub_rn(p.x, pos.x), __fsub_rn(p.y, pos.y), __fsub_rn(p.z, pos.z));
     float inv = rsqrtf(dot3(dp, dp));
-    f3 dir = mk3(dp.x * inv, dp.y * inv, dp.z * inv);
+    f3 dir = mk3(pmul(dp.x, inv), pmul(dp.y, inv), pmul(dp.z, inv));
     float cosinus = -dot3(n, dir);
     if (cosinus < 1e-5f) return mk3(0, 0, 0); // facing back: failed sample
     return dir;

@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                     uint32_t j = basepos + __popc(ballot & lt_mask);
                     f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), t);
                     float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
-                    C.hit_a[j] = make_float4(p.x, p.y, p.z, ro.w);
-                    C.hit_b[j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+                    C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, ro.w);
+                    C.hit_b[depth & 1][j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
                 }
             }
         }

@@ -47,7 +47,7 @@ def test_c2_fused_equals_queued_at_full_size(cornell):
     b = sc.render_host(capi.default_params(pass_count=1, flags=capi.FLAG_NO_FUSED_LAST_LEVEL, **C2))
     assert close(a[0], b[0]) and np.array_equal(a[2], b[2])
     assert a[3].rays == b[3].rays and a[3].light_hits == b[3].light_hits and list(a[3].rays_at_depth) == list(b[3].rays_at_depth)
-    assert a[3].rays_resolved_in_shade == a[3].rays_at_depth[3] > 0 and b[3].rays_resolved_in_shade == 0
+    assert a[3].rays_resolved_in_shade == a[3].rays - a[3].paths > 0 and b[3].rays_resolved_in_shade == 0
 
 
 def test_c2_image_is_linear_in_the_emitted_power(cornell):

@@ -117,20 +117,26 @@ def test_zero_weight_pruning_preserves_the_image(scenes):
                                      ("box", dict(depth_max=2, schedule=[5, 3])), ("box", dict(depth_max=1)),
                                      ("cornell", dict(depth_max=3, schedule=[4, 0, 2]))])
 def test_fused_last_level_equals_queued_last_level(name, kw, scenes):
-    """The shade kernel that resolves its own children (default on analytic scenes) against the queue + k_extend<LAST>
-    path (IPT_FLAG_NO_FUSED_LAST_LEVEL): same rays, same hits; sums equal up to the order of the float atomics."""
+    """The shade kernels that trace their own children (default on analytic scenes: every depth, shadow rays at the last)
+    against the queue + k_extend path, for the last level only (IPT_FLAG_NO_FUSED_TRACE) and for all levels
+    (IPT_FLAG_NO_FUSED_LAST_LEVEL): same rays, same hits; sums equal up to the order of the float atomics."""
     sd, sc = scenes(name)
     base = dict(width=64, height=64, pass_count=3, plane_mode=capi.PLANE_LINEAR)
     base.update(kw)
     a = sc.render_host(capi.default_params(**base))
+    m = sc.render_host(capi.default_params(flags=capi.FLAG_NO_FUSED_TRACE, **base))
     b = sc.render_host(capi.default_params(flags=capi.FLAG_NO_FUSED_LAST_LEVEL, **base))
-    assert np.allclose(a[0], b[0], rtol=2e-5, atol=1e-7) and np.allclose(a[1], b[1], rtol=5e-5, atol=1e-7)
-    assert np.array_equal(a[2], b[2])
-    for f in ("rays", "light_hits", "surface_hits", "misses", "failed_samples", "zero_weight_pruned", "nonfinite_dropped"):
-        assert getattr(a[3], f) == getattr(b[3], f), f
-    assert list(a[3].rays_at_depth) == list(b[3].rays_at_depth)
+    for x in (m, b):
+        assert np.allclose(a[0], x[0], rtol=2e-5, atol=1e-7) and np.allclose(a[1], x[1], rtol=5e-5, atol=1e-7)
+        assert np.array_equal(a[2], x[2])
+        for f in ("rays", "light_hits", "surface_hits", "misses", "failed_samples", "zero_weight_pruned", "nonfinite_dropped"):
+            assert getattr(a[3], f) == getattr(x[3], f), f
+        assert list(a[3].rays_at_depth) == list(x[3].rays_at_depth)
+    assert b[3].rays_resolved_in_shade == 0
     if base.get("depth_max", 4) >= 2 and base.get("schedule", [1])[-1] != 0:
-        assert a[3].kernel_launches < b[3].kernel_launches
+        assert a[3].kernel_launches <= m[3].kernel_launches < b[3].kernel_launches
+        assert a[3].rays_resolved_in_shade == a[3].rays - a[3].paths      # everything but the camera rays
+        assert m[3].rays_resolved_in_shade <= a[3].rays_resolved_in_shade
 
 
 def test_batching_and_tiles_are_invisible(scenes):

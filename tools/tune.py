@@ -4,6 +4,8 @@ sys.path.insert(0, '.')
 from ipt_b200 import build
 variants = {
     "base": [],
+    "next2": ["IPT_SHADE_NEXT_MIN_BLOCKS=2"],
+    "next4": ["IPT_SHADE_NEXT_MIN_BLOCKS=4"],
     "fused2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2"],
     "fused3": ["IPT_SHADE_FUSED_MIN_BLOCKS=3"],
     "fused4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
