@@ -342,15 +342,17 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         # dominant kernel and its algorithmic bytes: the wavefront MODEL of SURVEY.md §8d — every ray
         # is a 36 B record written once and read once, every queued hit a 32 B record written once and read once.
-        # The fused shade kernel resolves the last traced depth without queueing it: it is credited with the model bytes
-        # of the two kernels it replaces (36 B write + 36 B read per such ray + 8 B per light hit), and
-        # `implemented_bytes_per_launch` says what the implementation itself has to move.
+        # The fused shade kernels trace the children they spawn, so those rays are never queued: a fused launch is
+        # credited with the model bytes of the two kernels it replaces (36 B write + 36 B read per such ray, the hit
+        # record it appends, 8 B per light hit), and `implemented_bytes_per_launch` says what the implementation itself
+        # has to move (hit records in and out, path values).
         children = agg["rays"] - agg["paths"]
         queued = (agg["queue_bytes"] - 72 * agg["rays"] - 8 * agg["paths"]) // 64
         fused = agg["fused"]
-        bytes_ext = 36 * (agg["rays"] - fused) + 32 * queued + 8 * agg["light"] + 64 * (agg["nodes"] + agg["tris"])  # + BVH nodes / triangle records
-        bytes_shade = 32 * queued + 36 * children + 36 * fused
-        bytes_shade_impl = 32 * queued + 36 * (children - fused)
+        hits_by_shade = max(queued - agg["paths"], 0) if fused == children and fused else 0  # all but the camera rays' hits
+        bytes_ext = 36 * (agg["rays"] - fused) + 32 * (queued - hits_by_shade) + 8 * agg["light"] * (0 if fused else 1) + 64 * (agg["nodes"] + agg["tris"])
+        bytes_shade = 32 * queued + 36 * children + 36 * fused + 32 * hits_by_shade + 8 * agg["light"] * (1 if fused else 0)
+        bytes_shade_impl = 32 * queued + 36 * (children - fused) + 32 * hits_by_shade + 8 * agg["light"] * (1 if fused else 0)
         dom = "shade" if agg["ms_shade"] >= agg["ms_ext"] else "extend"
         dom_ms = agg["ms_shade"] if dom == "shade" else agg["ms_ext"]
         dom_n = agg["n_shade"] if dom == "shade" else agg["n_ext"]
@@ -370,7 +372,7 @@ def run_ours(args):
             "config": {"workload": workload_text(), "passes_per_step": pps, "paths_per_step_per_gpu": paths_per_pass * pps,
                        "parallelism": f"pass-sharded x{world}" if world > 1 else "single GPU",
                        "l2": "per-step ray/hit queue working set (>1 GB) exceeds the 126 MB L2; no flush needed",
-                       "batch_paths": args.batch_paths or "library default (2^27 / widest queued tree level)"},
+                       "batch_paths": args.batch_paths or "library default (2^28 / widest queued tree level = 2^21 paths)"},
             "mrays_per_s": rays_all / elapsed / 1e6, "rays_per_path": rays_all / max(paths_all, 1), "image_mean": image_mean,
             "device_ms_per_step": agg["ms_dev"] / args.steps,
             "clocks": clocks,

@@ -951,8 +951,10 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     // default batch: as many paths as keep the widest tree level near 2^28 rays (2^19 paths at 16/8/4/2; up to 2^23
     // for narrow schedules such as depth 8 with one child per hit, whose deeper levels would otherwise be tiny launches)
     // (with the fused last level the widest level is not queued: 2^27 / widest queued level, i.e. 2^20 paths at 16/8/4/2)
-    uint64_t batch_rays = max_queued_w < max_ray_w ? (1ull << 27) : (1ull << 28);
-    uint64_t batch_w = fuse_next ? max_hit_w : max_queued_w; // fused: what is queued are the hits
+    // (fused shade kernels: what is queued are the hits, 2^28 / widest hit level = 2^21 paths at 16/8/4/2, 17 GB of
+    // hit records in the two sets; 2^20 paths is 1.5 % slower, 2^22 0.3 % faster)
+    uint64_t batch_rays = (max_queued_w < max_ray_w && !fuse_next) ? (1ull << 27) : (1ull << 28);
+    uint64_t batch_w = fuse_next ? max_hit_w : max_queued_w;
     uint64_t batch = p->batch_paths ? p->batch_paths : std::min<uint64_t>(1ull << 23, std::max<uint64_t>(1ull << 16, batch_rays / batch_w));
     batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
     const uint64_t budget = 24ull << 30; // bytes of queue memory
