@@ -94,6 +94,7 @@ struct ipt_scene {
     DevScene dev{};
     DevPrim* d_prims = nullptr;
     DevLight* d_lights = nullptr;
+    float* d_light_cdf = nullptr;
     DevMaterial* d_mats = nullptr;
     LbvhDevice bvh{};
     LbvhDevice light_bvh{};
@@ -456,6 +457,12 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     CUDA_TRY(upload(s->d_mats, mats));
     dv.prims_g = s->d_prims;
     dv.lights_g = s->d_lights;
+    {
+        std::vector<float> cdf(lights.size());
+        for (size_t i = 0; i < lights.size(); ++i) cdf[i] = lights[i].cdf;
+        CUDA_TRY(upload(s->d_light_cdf, cdf));
+        dv.light_cdf = s->d_light_cdf;
+    }
     dv.mats_g = s->d_mats;
     for (uint32_t i = 0; i < desc->n_prims && i < IPT_INLINE_PRIMS; ++i) dv.prims[i] = prims[i];
     for (uint32_t i = 0; i < desc->n_lights && i < IPT_INLINE_LIGHTS; ++i) dv.lights[i] = lights[i];
@@ -555,7 +562,7 @@ int ipt_scene_destroy(ipt_scene* s) {
     free_workspace(s->ws);
     lbvh_free(s->bvh);
     lbvh_free(s->light_bvh);
-    cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
+    cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_light_cdf); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
     if (s->pinned) cudaFreeHost(s->pinned);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     cudaEventDestroy(s->ev_begin); cudaEventDestroy(s->ev_end);

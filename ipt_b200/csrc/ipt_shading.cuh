@@ -253,10 +253,10 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
         uint32_t lo = 0, hi = S.n_lights;
         while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
-            if (us < S.lights_g[mid].cdf) hi = mid; else lo = mid + 1;
+            if (us < __ldg(&S.light_cdf[mid])) hi = mid; else lo = mid + 1;
         }
         if (lo < S.n_lights) { from_light = true; wl = light_sample_dir(S.lights_g[lo], pos, u1, u2); }
-        acc = S.lights_g[S.n_lights - 1].cdf;
+        acc = __ldg(&S.light_cdf[S.n_lights - 1]);
     }
     f3 ws = sdf_sample(sdf, bn, bl, u1, u2, ul);
     if (from_light) return wl;
