@@ -455,9 +455,7 @@ int ipt_plane_display(ipt_plane* p, float glare_cutoff, float* out, float* ms) {
     CUDA_TRY(ws.glare.ensure(4 * n));
     CUDA_TRY(ws.shown.ensure(4 * n));
     float *d_mean = ws.mean.as<float>(), *d_glare = ws.glare.as<float>(), *d_norm = ws.shown.as<float>();
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
+    cudaEvent_t e0 = p->scene->ev_begin, e1 = p->scene->ev_end; // the scene's own pair (the lock is held)
     CUDA_TRY(cudaEventRecord(e0, st));
     k_plane_resolve<<<iptd::grid_for(n, 256), 256, 0, st>>>(p->sum, p->count, n, d_mean);
     int rc = iptd::device_glare(ws, d_mean, p->width, p->height, glare_cutoff, d_glare, st, nullptr); // gui.cpp:84
@@ -469,8 +467,6 @@ int ipt_plane_display(ipt_plane* p, float glare_cutoff, float* out, float* ms) {
         if (e != cudaSuccess) rc = fail(IPT_ERR_CUDA, cudaGetErrorString(e));
         else if (ms) cudaEventElapsedTime(ms, e0, e1);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return rc;
 }
 
