@@ -440,6 +440,32 @@ __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCt
     } else ++n_surface;
 }
 
+// First node visit of the light LBVH: false = the ray misses both root boxes, i.e. there is no light along it.
+__device__ __forceinline__ bool light_root_hit(const DevScene& S, f3 o, f3 d) {
+    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    f8 n0 = ldg256(&S.light_nodes[0]);
+    f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[0]) + 32);
+    return light_box(n0, 0, o, inv, IPT_INF) || light_box(n1, 0, o, inv, IPT_INF);
+}
+// Many-light scenes, last traced depth: the whole of trace_scene_last for a parked ray (light LBVH walk, weight, and the
+// occlusion test if a light was reached). Parked are only rays that passed light_root_hit, so the lanes of a pop walk
+// the LBVH together instead of idling next to the rays that leave at the root.
+template <bool SMALLPT>
+__device__ __forceinline__ void last_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, TraceCounters& tc,
+                                            uint32_t& n_light, uint32_t& n_surface, uint32_t& n_dropped) {
+    f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
+    f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
+    Outcome oc = trace_scene_last<SMALLPT, false>(S, o, d, tc);
+    float wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
+    if (!isfinite(wr)) ++n_dropped;
+    else if (oc.kind == 2) {
+        ++n_light;
+        float power = S.light_inline ? S.lights[oc.light].surface_power : S.lights_g[oc.light].surface_power;
+        if (!isfinite(power)) power = 1.0f; // main.cpp:123 point-light hack
+        atomicAdd(&C.pathval[__float_as_uint(dq[10 * IPT_PARK + k])], wr * power);
+    } else if (oc.kind == 1) ++n_surface;
+}
+
 struct ExtendCounters {
     uint32_t surface, light, miss, dropped;
 };
@@ -594,6 +620,33 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                 // the body of k_extend<LAST> for this ray, in two steps: the light test now; the occlusion test of the
                 // rays that did reach a light (about a third) is parked in a per-warp shared-memory queue and run 32 at a
                 // time, so the geometry intersection is issued for full warps instead of for the third of the lanes
+                if (S.n_light_bvh > 1) {
+                    // many lights: regroup BEFORE the light-LBVH walk. A ray that misses the root boxes sees no light and,
+                    // at the last traced depth, is done; the others are parked and walk the LBVH 32 at a time.
+                    bool parkb = false;
+                    if (emit) {
+                        ++n_fused;
+                        parkb = light_root_hit(S, pos, w);
+                    }
+                    uint32_t pbb = __ballot_sync(0xffffffffu, parkb);
+                    if (pbb) {
+                        if (parkb) {
+                            uint32_t k = qn + __popc(pbb & ((1u << lane) - 1u));
+                            dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
+                            dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
+                            dq[6 * IPT_PARK + k] = wgt; dq[7 * IPT_PARK + k] = child_sv;
+                            dq[10 * IPT_PARK + k] = __uint_as_float(tag & C.slot_mask);
+                        }
+                        qn += __popc(pbb);
+                        __syncwarp();
+                        if (qn >= 32) {
+                            qn -= 32;
+                            last_parked<SMALLPT>(S, C, dq, qn + lane, tc, n_light, n_surface, n_dropped);
+                            __syncwarp();
+                        }
+                    }
+                    continue;
+                }
                 bool park = false;
                 float contrib = 0.0f;
                 f3 lpos = mk3(0, 0, 0);
@@ -646,7 +699,10 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             }
         }
     }
-    if (FUSE == FUSE_LAST && lane < qn) resolve_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface); // drain
+    if (FUSE == FUSE_LAST && lane < qn) { // drain
+        if (S.n_light_bvh > 1) last_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
+        else resolve_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface);
+    }
     if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
     n_light += ec.light; n_surface += ec.surface; n_dropped += ec.dropped;
     flush_stat(C.stats, ST_FAILED, n_failed);

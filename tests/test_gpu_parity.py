@@ -114,6 +114,7 @@ def test_zero_weight_pruning_preserves_the_image(scenes):
 
 
 @pytest.mark.parametrize("name,kw", [("box", {}), ("cornell", {}), ("smallpt", {}), ("mixedlights", {}), ("lightgrid:3x3", {}),
+                                     ("lightgrid:5x6", {}),  # > 8 lights: light LBVH, last-level rays regrouped before the walk
                                      ("box", dict(depth_max=2, schedule=[5, 3])), ("box", dict(depth_max=1)),
                                      ("cornell", dict(depth_max=3, schedule=[4, 0, 2]))])
 def test_fused_last_level_equals_queued_last_level(name, kw, scenes):
