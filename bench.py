@@ -360,7 +360,7 @@ def run_ours(args):
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         traffic = None
         prof = ROOT / "profiles" / "roofline_latest.json"
-        if prof.exists():
+        if prof.exists() and args.workload == "c2" and not args.batch_paths:  # the ncu capture is of this workload at the default batch
             try:
                 traffic = json.loads(prof.read_text()).get(dom, {}).get("dram_bytes_per_launch")
             except Exception:
