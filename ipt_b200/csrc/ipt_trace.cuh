@@ -177,13 +177,13 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 // trace_scene / trace_scene_last.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef IPT_REFILL_MIN
-#define IPT_REFILL_MIN 8    // fetch new rays when at least this many lanes are idle
+#define IPT_REFILL_MIN 4    // fetch new rays when at least this many lanes are idle
 #endif
 #ifndef IPT_TRAV_STEPS
-#define IPT_TRAV_STEPS 12    // node visits between two refill checks
+#define IPT_TRAV_STEPS 16    // node visits between two refill checks
 #endif
 #ifndef IPT_LEAF_BATCH
-#define IPT_LEAF_BATCH 10   // run the postponed triangle tests once this many lanes hold one
+#define IPT_LEAF_BATCH 6    // run the postponed triangle tests once this many lanes hold one
 #endif
 
 #ifndef IPT_MESH_MIN_BLOCKS
