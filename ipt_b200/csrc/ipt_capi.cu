@@ -532,8 +532,13 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     size_t sm = stack_smem(s);
     s->grid_generate = occupancy_grid(k_generate, s->sm_count, 0);
     s->grid_shade = occupancy_grid(k_shade<FUSE_NONE, false>, s->sm_count, 0);
-    s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0) : occupancy_grid(k_shade<FUSE_LAST, false>, s->sm_count, 0);
-    s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0) : occupancy_grid(k_shade<FUSE_NEXT, false>, s->sm_count, 0);
+    // (SmallPt scenes keep the runtime light switch; the others get the kernel compiled for their kind of light set)
+    s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0)
+                          : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_LAST, false, LB_YES>, s->sm_count, 0)
+                                           : occupancy_grid(k_shade<FUSE_LAST, false, LB_NO>, s->sm_count, 0);
+    s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0)
+                         : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_YES>, s->sm_count, 0)
+                                          : occupancy_grid(k_shade<FUSE_NEXT, false, LB_NO>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
         s->grid_mesh = occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
@@ -1055,13 +1060,15 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
             if (child_last && fuse_last) {
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else TIMED(2, (k_shade<FUSE_LAST, false><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, LB_YES><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_LAST, false, LB_NO><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 break;
             }
             if (fuse_next && width_at[d + 1] != 0) {
                 int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else TIMED(2, (k_shade<FUSE_NEXT, false><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, LB_YES><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_NEXT, false, LB_NO><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 traced = true; // the rays of depth d+1 are traced by this launch: no k_extend for them
                 continue;
             }

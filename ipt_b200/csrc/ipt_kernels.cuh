@@ -236,16 +236,22 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
 // nearest light, scanning in list order with strict `>` (CollectionLighting.cpp:23-34); `lpdf` receives the light part
 // of the mixture density along the same ray, sum_i w_i * DdfFromLight_i::value(d) (lighting.cpp:61-73, ddf.cpp:156-162),
 // which needs exactly the intersections this scan performs (PDF = false: nearest light only)
-template <bool PDF = true>
+// LB: whether the scene's lights sit in an LBVH — LB_RUNTIME asks the scene, LB_NO / LB_YES are the compile-time answers
+// the fused shade kernels are instantiated with (each carries only the light code its scenes run).
+enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2 };
+template <int LB>
+__device__ __forceinline__ bool has_light_bvh(const DevScene& S) { return LB == LB_RUNTIME ? S.n_light_bvh != 0 : LB == LB_YES; }
+template <bool PDF = true, int LB = LB_RUNTIME>
 __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& lpdf) {
     bool any = false;
     float best_len = 0.0f;
     lpdf = 0.0f;
-    if (S.n_light_bvh) {
+    if (has_light_bvh<LB>(S)) {
         if (PDF) lpdf = light_bvh_query<LQ_BOTH>(S, o, d, which, lpos);
         else light_bvh_query<LQ_NEAREST>(S, o, d, which, lpos);
         return which != IPT_NO_HIT;
     }
+    if (LB == LB_YES) return false; // unreachable: the LBVH branch above always returns
     if (S.light_inline) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
@@ -265,13 +271,13 @@ struct Outcome {
 };
 
 // Geometry::traceRay + Lighting::traceRayToLight + the decision of main.cpp:111-128
-template <bool SMALLPT, bool MESH>
+template <bool SMALLPT, bool MESH, int LB = LB_RUNTIME>
 __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
     r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
-    bool lh = trace_lights(S, o, d, r.light, r.light_pos, r.light_pdf);
+    bool lh = trace_lights<true, LB>(S, o, d, r.light, r.light_pos, r.light_pdf);
     bool sh = r.surf.prim != IPT_NO_HIT;
     r.kind = 0;
     if (lh) {
@@ -290,13 +296,13 @@ __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, Tr
 // a light before any surface. Lights are tested first and the geometry only for rays that hit one ("shadow ray"):
 // the decision is the same expression as in trace_scene, evaluated for fewer rays. kind 3 = no light along the ray
 // (surface or miss, not resolved).
-template <bool SMALLPT, bool MESH>
+template <bool SMALLPT, bool MESH, int LB = LB_RUNTIME>
 __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
     r.surf.prim = IPT_NO_HIT; r.surf.t = IPT_INF; r.surf.tri_pos = IPT_NO_HIT;
-    bool lh = trace_lights(S, o, d, r.light, r.light_pos, r.light_pdf);
+    bool lh = trace_lights<true, LB>(S, o, d, r.light, r.light_pos, r.light_pdf);
     r.kind = 3;
     if (!lh) return r;
     r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
@@ -455,7 +461,7 @@ __device__ __forceinline__ void last_parked(const DevScene& S, const RenderCtx& 
                                             uint32_t& n_light, uint32_t& n_surface, uint32_t& n_dropped) {
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
-    Outcome oc = trace_scene_last<SMALLPT, false>(S, o, d, tc);
+    Outcome oc = trace_scene_last<SMALLPT, false, LB_YES>(S, o, d, tc);
     float wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
     if (!isfinite(wr)) ++n_dropped;
     else if (oc.kind == 2) {
@@ -472,7 +478,7 @@ struct ExtendCounters {
 // The body of k_extend<.., LAST = false> for one parked child ray of depth `depth` (entry k of the warp's queue; all 32
 // lanes call this, `valid` masks the drain): trace_scene, weight resolution, emission, and the warp-aggregated append
 // of the surface hits to the hit set of `depth`.
-template <bool SMALLPT>
+template <bool SMALLPT, int LB>
 __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, bool valid, uint32_t depth,
                                               TraceCounters& tc, ExtendCounters& ec) {
     const uint32_t lane = threadIdx.x & 31;
@@ -485,7 +491,7 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
         o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
         d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
         ctag = __float_as_uint(dq[8 * IPT_PARK + k]);
-        oc = trace_scene<SMALLPT, false>(S, o, d, tc);
+        oc = trace_scene<SMALLPT, false, LB>(S, o, d, tc);
         wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
         if (!isfinite(wr)) ++ec.dropped; // non-finite multiplier (main.cpp:175): drop this sample
         else if (oc.kind == 2) {
@@ -523,7 +529,7 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
 //              light test at once, and only the rays that reach a light are parked for the occlusion test.
 // Same functions, same operands, same counters as the separate kernels.
 enum ShadeFusion { FUSE_NONE = 0, FUSE_NEXT = 1, FUSE_LAST = 2 };
-template <int FUSE, bool SMALLPT>
+template <int FUSE, bool SMALLPT, int LB = LB_RUNTIME>
 __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : FUSE == FUSE_NEXT ? IPT_SHADE_NEXT_MIN_BLOCKS : IPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth + 1];
     const uint32_t lane = threadIdx.x & 31;
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     __syncwarp();
                     if (qn >= 32) {
                         qn -= 32;
-                        extend_parked<SMALLPT>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
+                        extend_parked<SMALLPT, LB>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
                         __syncwarp();
                     }
                 }
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                 // the body of k_extend<LAST> for this ray, in two steps: the light test now; the occlusion test of the
                 // rays that did reach a light (about a third) is parked in a per-warp shared-memory queue and run 32 at a
                 // time, so the geometry intersection is issued for full warps instead of for the third of the lanes
-                if (S.n_light_bvh > 1) {
+                if (has_light_bvh<LB>(S)) {
                     // many lights: regroup BEFORE the light-LBVH walk. A ray that misses the root boxes sees no light and,
                     // at the last traced depth, is done; the others are parked and walk the LBVH 32 at a time.
                     bool parkb = false;
@@ -654,7 +660,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     ++n_fused;
                     uint32_t li = IPT_NO_HIT;
                     float lpdf;
-                    bool lh = trace_lights(S, pos, w, li, lpos, lpdf);
+                    bool lh = trace_lights<true, LB == LB_RUNTIME ? LB_RUNTIME : LB_NO>(S, pos, w, li, lpos, lpdf);
                     float wr = resolve_weight(S, wgt, child_sv, lpdf);
                     if (!isfinite(wr)) ++n_dropped;
                     else if (lh) {
@@ -700,10 +706,10 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
         }
     }
     if (FUSE == FUSE_LAST && lane < qn) { // drain
-        if (S.n_light_bvh > 1) last_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
+        if (has_light_bvh<LB>(S)) last_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
         else resolve_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface);
     }
-    if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
+    if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT, LB>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
     n_light += ec.light; n_surface += ec.surface; n_dropped += ec.dropped;
     flush_stat(C.stats, ST_FAILED, n_failed);
     flush_stat(C.stats, ST_PRUNED, n_pruned);
