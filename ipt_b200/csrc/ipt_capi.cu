@@ -535,9 +535,11 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     // (SmallPt scenes keep the runtime light switch; the others get the kernel compiled for their kind of light set)
     s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0)
                           : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_LAST, false, LB_YES>, s->sm_count, 0)
-                                           : occupancy_grid(k_shade<FUSE_LAST, false, LB_NO>, s->sm_count, 0);
+                          : dv.light_inline ? occupancy_grid(k_shade<FUSE_LAST, false, LB_INLINE>, s->sm_count, 0)
+                                            : occupancy_grid(k_shade<FUSE_LAST, false, LB_NO>, s->sm_count, 0);
     s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0)
                          : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_YES>, s->sm_count, 0)
+                         : dv.light_inline ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE>, s->sm_count, 0)
                                           : occupancy_grid(k_shade<FUSE_NEXT, false, LB_NO>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
@@ -1061,6 +1063,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, LB_YES><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, LB_INLINE><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else TIMED(2, (k_shade<FUSE_LAST, false, LB_NO><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 break;
             }
@@ -1068,6 +1071,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, LB_YES><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, LB_INLINE><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else TIMED(2, (k_shade<FUSE_NEXT, false, LB_NO><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 traced = true; // the rays of depth d+1 are traced by this launch: no k_extend for them
                 continue;

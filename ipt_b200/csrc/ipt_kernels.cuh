@@ -238,9 +238,17 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
 // which needs exactly the intersections this scan performs (PDF = false: nearest light only)
 // LB: whether the scene's lights sit in an LBVH — LB_RUNTIME asks the scene, LB_NO / LB_YES are the compile-time answers
 // the fused shade kernels are instantiated with (each carries only the light code its scenes run).
-enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2 };
+// LB_INLINE: no LBVH and at most IPT_INLINE_LIGHTS lights, i.e. the constant-bank copies (every reference scene).
+enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2, LB_INLINE = 3 };
 template <int LB>
 __device__ __forceinline__ bool has_light_bvh(const DevScene& S) { return LB == LB_RUNTIME ? S.n_light_bvh != 0 : LB == LB_YES; }
+template <int LB>
+__device__ __forceinline__ bool lights_inline(const DevScene& S) { return LB == LB_INLINE ? true : LB == LB_YES ? false : S.light_inline != 0; }
+template <int LB>
+__device__ __forceinline__ float light_power(const DevScene& S, uint32_t i) {
+    float power = lights_inline<LB>(S) ? S.lights[i].surface_power : S.lights_g[i].surface_power;
+    return isfinite(power) ? power : 1.0f; // main.cpp:123 point-light hack
+}
 template <bool PDF = true, int LB = LB_RUNTIME>
 __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& lpdf) {
     bool any = false;
@@ -252,11 +260,11 @@ __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint
         return which != IPT_NO_HIT;
     }
     if (LB == LB_YES) return false; // unreachable: the LBVH branch above always returns
-    if (S.light_inline) {
+    if (lights_inline<LB>(S)) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
             if (i < (int)S.n_lights) trace_one_light<PDF>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
-    } else {
+    } else if (LB != LB_INLINE) {
         for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light<PDF>(S.lights_g[i], i, o, d, any, best_len, which, lpos, lpdf);
     }
     return any;
@@ -496,9 +504,7 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
         if (!isfinite(wr)) ++ec.dropped; // non-finite multiplier (main.cpp:175): drop this sample
         else if (oc.kind == 2) {
             ++ec.light;
-            float power = S.light_inline ? S.lights[oc.light].surface_power : S.lights_g[oc.light].surface_power;
-            if (!isfinite(power)) power = 1.0f; // main.cpp:123 point-light hack
-            atomicAdd(&C.pathval[ctag & C.slot_mask], wr * power);
+            atomicAdd(&C.pathval[ctag & C.slot_mask], wr * light_power<LB>(S, oc.light));
         } else if (oc.kind == 1) {
             ++ec.surface;
             emit = true;
@@ -586,7 +592,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
-                w = mix_sample(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                w = mix_sample<LB == LB_INLINE>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
                     if (C.flags & 4u) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
@@ -660,13 +666,11 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     ++n_fused;
                     uint32_t li = IPT_NO_HIT;
                     float lpdf;
-                    bool lh = trace_lights<true, LB == LB_RUNTIME ? LB_RUNTIME : LB_NO>(S, pos, w, li, lpos, lpdf);
+                    bool lh = trace_lights<true, LB == LB_YES ? LB_NO : LB>(S, pos, w, li, lpos, lpdf);
                     float wr = resolve_weight(S, wgt, child_sv, lpdf);
                     if (!isfinite(wr)) ++n_dropped;
                     else if (lh) {
-                        float power = S.light_inline ? S.lights[li].surface_power : S.lights_g[li].surface_power;
-                        if (!isfinite(power)) power = 1.0f; // main.cpp:123 point-light hack
-                        contrib = wr * power;
+                        contrib = wr * light_power<LB>(S, li);
                         park = true;
                     }
                 }

@@ -237,18 +237,20 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
 // UnionDdf::sample (src/libddf/ddf.cpp:138-154): scan the running float sum of weights with one draw `us`; the first
 // component whose running sum exceeds it is sampled. r >= total (float rounding; uninitialised result in the
 // reference) is a failed sample. Both candidate directions are formed by every lane (no light-vs-sdf divergence).
+// INLINE_LIGHTS: 1 = the caller knows the lights are the inline ones (compile-time), 0 = ask the scene
+template <int INLINE_LIGHTS = 0>
 __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, const Basis& bl, f3 pos, float us, float u1, float u2, float ul) {
     f3 wl = mk3(0, 0, 0);
     float acc = 0.0f;
     bool from_light = false;
-    if (S.light_inline) {
+    if (INLINE_LIGHTS || S.light_inline) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i)
             if (i < (int)S.n_lights) {
                 acc = S.lights[i].cdf;
                 if (!from_light && us < acc) { from_light = true; wl = light_sample_dir(S.lights[i], pos, u1, u2); }
             }
-    } else if (S.n_lights) {
+    } else if (!INLINE_LIGHTS && S.n_lights) {
         // first i with us < cdf[i]; cdf is non-decreasing, so a binary search finds what the linear scan finds
         uint32_t lo = 0, hi = S.n_lights;
         while (lo < hi) {
