@@ -99,6 +99,7 @@ struct ipt_scene {
     LbvhDevice bvh{};
     LbvhDevice light_bvh{};
     bool smallpt = false, mesh = false;
+    bool inline_area_light = false; // the scene's lights are the inline ones and all of them are area lights
     Workspace ws;
     uint32_t* d_cnt = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -445,6 +446,9 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     dv.sdf_weight = sdf_weight;
     dv.prim_inline = desc->n_prims <= IPT_INLINE_PRIMS;
     dv.light_inline = desc->n_lights <= IPT_INLINE_LIGHTS;
+    s->inline_area_light = dv.light_inline && desc->n_lights > 0;
+    for (uint32_t i = 0; i < desc->n_lights && i < IPT_INLINE_LIGHTS; ++i)
+        if (desc->lights[i].kind > IPT_LIGHT_AREA_TRIANGLE) s->inline_area_light = false;
     auto upload = [&](auto*& dptr, const auto& vec) -> cudaError_t {
         size_t bytes = std::max<size_t>(vec.size(), 1) * sizeof(vec[0]);
         cudaError_t e = cudaMalloc((void**)&dptr, bytes);
@@ -535,11 +539,13 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     // (SmallPt scenes keep the runtime light switch; the others get the kernel compiled for their kind of light set)
     s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0)
                           : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_LAST, false, LB_YES>, s->sm_count, 0)
+                          : s->inline_area_light ? occupancy_grid(k_shade<FUSE_LAST, false, LB_INLINE_AREA>, s->sm_count, 0)
                           : dv.light_inline ? occupancy_grid(k_shade<FUSE_LAST, false, LB_INLINE>, s->sm_count, 0)
                                             : occupancy_grid(k_shade<FUSE_LAST, false, LB_NO>, s->sm_count, 0);
     s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0)
                          : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_YES>, s->sm_count, 0)
-                         : dv.light_inline ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE>, s->sm_count, 0)
+                         : s->inline_area_light ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE_AREA>, s->sm_count, 0)
+                          : dv.light_inline ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE>, s->sm_count, 0)
                                           : occupancy_grid(k_shade<FUSE_NEXT, false, LB_NO>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
@@ -1063,6 +1069,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, LB_YES><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_LAST, false, LB_INLINE_AREA><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, LB_INLINE><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else TIMED(2, (k_shade<FUSE_LAST, false, LB_NO><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 break;
@@ -1071,6 +1078,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, LB_YES><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_NEXT, false, LB_INLINE_AREA><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, LB_INLINE><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else TIMED(2, (k_shade<FUSE_NEXT, false, LB_NO><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 traced = true; // the rays of depth d+1 are traced by this launch: no k_extend for them

@@ -152,10 +152,10 @@ template <bool SMALLPT, bool MESH>
 __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc);
 
 // ---- nearest light (CollectionLighting::traceRayToLight, src/CollectionLighting.cpp:23-34) -----------
-template <bool PDF, class LightRef>
+template <bool PDF, bool AREA = false, class LightRef>
 __device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f3 o, f3 d, bool& any, float& best_len, uint32_t& which, f3& lpos,
                                                 float& lpdf) {
-    LightHit e = light_trace(L, o, d);
+    LightHit e = light_trace<AREA>(L, o, d);
     if (!e.hit) return;
     float len = xlength3(xsub3(e.position, o));
     if (!any || best_len > len) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f
         which = i;
         lpos = e.position;
     }
-    if (PDF) lpdf = pfma(L.weight, light_pdf_at(L, o, e.position), lpdf);
+    if (PDF) lpdf = pfma(L.weight, light_pdf_at<AREA>(L, o, e.position), lpdf);
 }
 // conservative ray/box test for the light LBVH (see slab() in ipt_trace.cuh); limit = farthest useful entry distance
 __device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, float limit) {
@@ -239,11 +239,12 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
 // LB: whether the scene's lights sit in an LBVH — LB_RUNTIME asks the scene, LB_NO / LB_YES are the compile-time answers
 // the fused shade kernels are instantiated with (each carries only the light code its scenes run).
 // LB_INLINE: no LBVH and at most IPT_INLINE_LIGHTS lights, i.e. the constant-bank copies (every reference scene).
-enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2, LB_INLINE = 3 };
+// LB_INLINE_AREA: ... and that light is an area light (no sphere-light code at all).
+enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2, LB_INLINE = 3, LB_INLINE_AREA = 4 };
 template <int LB>
 __device__ __forceinline__ bool has_light_bvh(const DevScene& S) { return LB == LB_RUNTIME ? S.n_light_bvh != 0 : LB == LB_YES; }
 template <int LB>
-__device__ __forceinline__ bool lights_inline(const DevScene& S) { return LB == LB_INLINE ? true : LB == LB_YES ? false : S.light_inline != 0; }
+__device__ __forceinline__ bool lights_inline(const DevScene& S) { return (LB == LB_INLINE || LB == LB_INLINE_AREA) ? true : LB == LB_YES ? false : S.light_inline != 0; }
 template <int LB>
 __device__ __forceinline__ float light_power(const DevScene& S, uint32_t i) {
     float power = lights_inline<LB>(S) ? S.lights[i].surface_power : S.lights_g[i].surface_power;
@@ -263,8 +264,8 @@ __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint
     if (lights_inline<LB>(S)) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
-            if (i < (int)S.n_lights) trace_one_light<PDF>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
-    } else if (LB != LB_INLINE) {
+            if (i < (int)S.n_lights) trace_one_light<PDF, LB == LB_INLINE_AREA>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
+    } else if (LB != LB_INLINE && LB != LB_INLINE_AREA) {
         for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light<PDF>(S.lights_g[i], i, o, d, any, best_len, which, lpos, lpdf);
     }
     return any;
@@ -592,9 +593,9 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
-                w = mix_sample<LB == LB_INLINE>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                w = mix_sample<LB == LB_INLINE || LB == LB_INLINE_AREA, LB == LB_INLINE_AREA>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
-                    if (C.flags & 4u) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
+                    if (FUSE == FUSE_NONE && (C.flags & 4u)) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
                 } else {
                     float sv = sdf_value(sdf, w);

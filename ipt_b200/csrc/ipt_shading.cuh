@@ -166,12 +166,13 @@ __device__ __forceinline__ float light_pdf(const DevLight& L, f3 pos, f3 w) {
 // The same density from an already known light hit (its position on light L along the ray from `pos`): what
 // DdfFromLight::value computes after its own light->traceRay (lighting.cpp:63-72). Used by k_extend, which has just
 // intersected the lights for this very ray, so the shading kernel does not have to trace the light a second time.
+template <bool AREA = false>
 __device__ __forceinline__ float light_pdf_at(const DevLight& L, f3 pos, f3 hit) {
     f3 dp = mk3(hit.x - pos.x, hit.y - pos.y, hit.z - pos.z);
     float decay = dot3(dp, dp);
     f3 n;
-    if (L.kind <= IPT_LIGHT_AREA_TRIANGLE) n = mk3(L.nx, L.ny, L.nz);
-    else {
+    if (AREA || L.kind <= IPT_LIGHT_AREA_TRIANGLE) n = mk3(L.nx, L.ny, L.nz);
+    else if (!AREA) {
         float ir = 1.0f / L.radius;
         n = mk3(pmul(__fsub_rn(hit.x, L.px), ir), pmul(__fsub_rn(hit.y, L.py), ir), pmul(__fsub_rn(hit.z, L.pz), ir));
         if (L.kind == IPT_LIGHT_SPHERE_INVERTED) n = neg3(n);
@@ -182,9 +183,10 @@ __device__ __forceinline__ float light_pdf_at(const DevLight& L, f3 pos, f3 hit)
 }
 
 // DdfFromLight::sample (src/lighting/lighting.cpp:50-59) over Light::sample (lighting.cpp:93-104, 172-207)
+template <bool AREA = false>
 __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float u1, float u2) {
     f3 p, n;
-    if (L.kind <= IPT_LIGHT_AREA_TRIANGLE) {
+    if (AREA || L.kind <= IPT_LIGHT_AREA_TRIANGLE) {
         float v2 = L.kind == IPT_LIGHT_AREA_TRIANGLE ? pmul(u2, __fsub_rn(1.0f, u1)) : u2;
         p = mk3(__fadd_rn(pfma(L.yax, v2, pmul(L.xax, u1)), L.px), __fadd_rn(pfma(L.yay, v2, pmul(L.xay, u1)), L.py),
                 __fadd_rn(pfma(L.yaz, v2, pmul(L.xaz, u1)), L.pz));
@@ -237,8 +239,8 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
 // UnionDdf::sample (src/libddf/ddf.cpp:138-154): scan the running float sum of weights with one draw `us`; the first
 // component whose running sum exceeds it is sampled. r >= total (float rounding; uninitialised result in the
 // reference) is a failed sample. Both candidate directions are formed by every lane (no light-vs-sdf divergence).
-// INLINE_LIGHTS: 1 = the caller knows the lights are the inline ones (compile-time), 0 = ask the scene
-template <int INLINE_LIGHTS = 0>
+// INLINE_LIGHTS: 1 = the caller knows the lights are the inline ones (compile-time), 0 = ask the scene; AREA: ... and area lights
+template <int INLINE_LIGHTS = 0, bool AREA = false>
 __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, const Basis& bl, f3 pos, float us, float u1, float u2, float ul) {
     f3 wl = mk3(0, 0, 0);
     float acc = 0.0f;
@@ -248,7 +250,7 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i)
             if (i < (int)S.n_lights) {
                 acc = S.lights[i].cdf;
-                if (!from_light && us < acc) { from_light = true; wl = light_sample_dir(S.lights[i], pos, u1, u2); }
+                if (!from_light && us < acc) { from_light = true; wl = light_sample_dir<AREA>(S.lights[i], pos, u1, u2); }
             }
     } else if (!INLINE_LIGHTS && S.n_lights) {
         // first i with us < cdf[i]; cdf is non-decreasing, so a binary search finds what the linear scan finds
