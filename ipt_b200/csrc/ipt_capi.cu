@@ -100,6 +100,7 @@ struct ipt_scene {
     LbvhDevice light_bvh{};
     bool smallpt = false, mesh = false;
     bool inline_area_light = false; // the scene's lights are the inline ones and all of them are area lights
+    bool geom_fast = false;         // grouped box planes + inline spheres only (analytic_closest's first branch)
     Workspace ws;
     uint32_t* d_cnt = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -493,6 +494,7 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     set_camera(dv, desc->camera);
     s->smallpt = smallpt;
     s->mesh = desc->n_triangles > 0;
+    s->geom_fast = !smallpt && !s->mesh && dv.planes_grouped && dv.others_inline;
     if (s->mesh) {
         std::string err;
         if (lbvh_build(desc->triangles, (uint32_t)desc->n_triangles, s->stream, s->bvh, err) != 0) {
@@ -539,12 +541,14 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     // (SmallPt scenes keep the runtime light switch; the others get the kernel compiled for their kind of light set)
     s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0)
                           : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_LAST, false, LB_YES>, s->sm_count, 0)
+                          : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_LAST, false, LB_REF>, s->sm_count, 0)
                           : s->inline_area_light ? occupancy_grid(k_shade<FUSE_LAST, false, LB_INLINE_AREA>, s->sm_count, 0)
                           : dv.light_inline ? occupancy_grid(k_shade<FUSE_LAST, false, LB_INLINE>, s->sm_count, 0)
                                             : occupancy_grid(k_shade<FUSE_LAST, false, LB_NO>, s->sm_count, 0);
     s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0)
                          : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_YES>, s->sm_count, 0)
-                         : s->inline_area_light ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE_AREA>, s->sm_count, 0)
+                         : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_REF>, s->sm_count, 0)
+                          : s->inline_area_light ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE_AREA>, s->sm_count, 0)
                           : dv.light_inline ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE>, s->sm_count, 0)
                                           : occupancy_grid(k_shade<FUSE_NEXT, false, LB_NO>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
@@ -1069,6 +1073,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, LB_YES><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_LAST, false, LB_REF><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_LAST, false, LB_INLINE_AREA><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, LB_INLINE><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else TIMED(2, (k_shade<FUSE_LAST, false, LB_NO><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
@@ -1078,6 +1083,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, LB_YES><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_NEXT, false, LB_REF><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_NEXT, false, LB_INLINE_AREA><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, LB_INLINE><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else TIMED(2, (k_shade<FUSE_NEXT, false, LB_NO><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));

@@ -148,7 +148,7 @@ struct TraceCounters {
     uint32_t nodes, tris;
 };
 
-template <bool SMALLPT, bool MESH>
+template <bool SMALLPT, bool MESH, bool GFAST = false>
 __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc);
 
 // ---- nearest light (CollectionLighting::traceRayToLight, src/CollectionLighting.cpp:23-34) -----------
@@ -240,11 +240,15 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
 // the fused shade kernels are instantiated with (each carries only the light code its scenes run).
 // LB_INLINE: no LBVH and at most IPT_INLINE_LIGHTS lights, i.e. the constant-bank copies (every reference scene).
 // LB_INLINE_AREA: ... and that light is an area light (no sphere-light code at all).
-enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2, LB_INLINE = 3, LB_INLINE_AREA = 4 };
+// LB_REF: ... and the geometry is grouped box planes + inline spheres (GFAST in ipt_trace.cuh): what every Lambert /
+// glossy box scene of the reference and of BASELINE configs[0..1] is.
+enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2, LB_INLINE = 3, LB_INLINE_AREA = 4, LB_REF = 5 };
+#define IPT_LB_IS_INLINE(LB) ((LB) == LB_INLINE || (LB) == LB_INLINE_AREA || (LB) == LB_REF)
+#define IPT_LB_IS_AREA(LB) ((LB) == LB_INLINE_AREA || (LB) == LB_REF)
 template <int LB>
 __device__ __forceinline__ bool has_light_bvh(const DevScene& S) { return LB == LB_RUNTIME ? S.n_light_bvh != 0 : LB == LB_YES; }
 template <int LB>
-__device__ __forceinline__ bool lights_inline(const DevScene& S) { return (LB == LB_INLINE || LB == LB_INLINE_AREA) ? true : LB == LB_YES ? false : S.light_inline != 0; }
+__device__ __forceinline__ bool lights_inline(const DevScene& S) { return IPT_LB_IS_INLINE(LB) ? true : LB == LB_YES ? false : S.light_inline != 0; }
 template <int LB>
 __device__ __forceinline__ float light_power(const DevScene& S, uint32_t i) {
     float power = lights_inline<LB>(S) ? S.lights[i].surface_power : S.lights_g[i].surface_power;
@@ -264,8 +268,8 @@ __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint
     if (lights_inline<LB>(S)) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
-            if (i < (int)S.n_lights) trace_one_light<PDF, LB == LB_INLINE_AREA>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
-    } else if (LB != LB_INLINE && LB != LB_INLINE_AREA) {
+            if (i < (int)S.n_lights) trace_one_light<PDF, IPT_LB_IS_AREA(LB)>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
+    } else if (!IPT_LB_IS_INLINE(LB)) {
         for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light<PDF>(S.lights_g[i], i, o, d, any, best_len, which, lpos, lpdf);
     }
     return any;
@@ -283,7 +287,7 @@ struct Outcome {
 template <bool SMALLPT, bool MESH, int LB = LB_RUNTIME>
 __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
-    r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
+    r.surf = trace_geometry<SMALLPT, MESH, LB == LB_REF>(S, o, d, tc);
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
     bool lh = trace_lights<true, LB>(S, o, d, r.light, r.light_pos, r.light_pdf);
@@ -314,7 +318,7 @@ __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 
     bool lh = trace_lights<true, LB>(S, o, d, r.light, r.light_pos, r.light_pdf);
     r.kind = 3;
     if (!lh) return r;
-    r.surf = trace_geometry<SMALLPT, MESH>(S, o, d, tc);
+    r.surf = trace_geometry<SMALLPT, MESH, LB == LB_REF>(S, o, d, tc);
     bool sh = r.surf.prim != IPT_NO_HIT;
     bool light_wins = !sh;
     if (sh) {
@@ -437,13 +441,13 @@ __device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, 
 #endif
 // Second half of trace_scene_last for a parked ray that reached a light at `lpos`: Geometry::traceRay and the
 // light-vs-surface decision of main.cpp:113; the light's contribution is added if nothing is nearer.
-template <bool SMALLPT>
+template <bool SMALLPT, int LB>
 __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, TraceCounters& tc,
                                                uint32_t& n_light, uint32_t& n_surface) {
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
     f3 lpos = mk3(dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], dq[8 * IPT_PARK + k]);
-    SurfHit sh = trace_geometry<SMALLPT, false>(S, o, d, tc);
+    SurfHit sh = trace_geometry<SMALLPT, false, LB == LB_REF>(S, o, d, tc);
     bool light_wins = sh.prim == IPT_NO_HIT;
     if (!light_wins) {
         f3 sp = xpoint(o, d, sh.t);
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
-                w = mix_sample<LB == LB_INLINE || LB == LB_INLINE_AREA, LB == LB_INLINE_AREA>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                w = mix_sample<IPT_LB_IS_INLINE(LB), IPT_LB_IS_AREA(LB)>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
                     if (FUSE == FUSE_NONE && (C.flags & 4u)) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
@@ -688,7 +692,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     __syncwarp();
                     if (qn >= 32) {
                         qn -= 32;
-                        resolve_parked<SMALLPT>(S, C, dq, qn + lane, tc, n_light, n_surface);
+                        resolve_parked<SMALLPT, LB>(S, C, dq, qn + lane, tc, n_light, n_surface);
                         __syncwarp();
                     }
                 }
@@ -712,7 +716,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
     }
     if (FUSE == FUSE_LAST && lane < qn) { // drain
         if (has_light_bvh<LB>(S)) last_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
-        else resolve_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface);
+        else resolve_parked<SMALLPT, LB>(S, C, dq, lane, tc, n_light, n_surface);
     }
     if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT, LB>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
     n_light += ec.light; n_surface += ec.surface; n_dropped += ec.dropped;

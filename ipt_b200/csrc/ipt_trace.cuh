@@ -116,15 +116,17 @@ extern __shared__ uint32_t ipt_dyn_smem[];
 
 // the ordered analytic primitive list: grouped planes + statically unrolled spheres when the scene allows, else the
 // generic ordered scan
-template <bool SMALLPT>
+// GFAST: the caller knows at compile time that the scene takes the first branch all the way (grouped planes and
+// inline spheres only), so none of the generic scans is instantiated
+template <bool SMALLPT, bool GFAST = false>
 __device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, double& dist_d, float& dist_f, uint32_t& best) {
-    if (!SMALLPT && S.planes_grouped) {
+    if (GFAST || (!SMALLPT && S.planes_grouped)) {
         if (S.n_planes) {
             isect_axis_planes(S.plane_of[0], S.plane_of[1], o.x, d.x, o, d, dist_f, best);
             isect_axis_planes(S.plane_of[2], S.plane_of[3], o.y, d.y, o, d, dist_f, best);
             isect_axis_planes(S.plane_of[4], S.plane_of[5], o.z, d.z, o, d, dist_f, best);
         }
-        if (S.others_inline) {
+        if (GFAST || S.others_inline) {
             // static indices: every sphere constant is an immediate constant-bank operand, no indexed LDC
 #pragma unroll
             for (int k = 0; k < IPT_INLINE_OTHERS; ++k) {
@@ -134,22 +136,22 @@ __device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, 
                     if (t < dist_f || (t == dist_f && t != IPT_INF && sp.index < best)) { dist_f = t; best = sp.index; }
                 }
             }
-        } else if (S.n_prims > S.n_planes) {
+        } else if (!GFAST && S.n_prims > S.n_planes) {
             if (S.prim_inline) trace_prim_list<false, true>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims[i]; }, o, d, dist_d, dist_f, best);
             else trace_prim_list<false, true>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims_g[i]; }, o, d, dist_d, dist_f, best);
         }
-    } else {
+    } else if (!GFAST) {
         if (S.prim_inline) trace_prim_list<SMALLPT, false>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims[i]; }, o, d, dist_d, dist_f, best);
         else trace_prim_list<SMALLPT, false>(S.n_prims, [&S](uint32_t i) -> const DevPrim& { return S.prims_g[i]; }, o, d, dist_d, dist_f, best);
     }
 }
 
-template <bool SMALLPT, bool MESH>
+template <bool SMALLPT, bool MESH, bool GFAST>
 __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     double dist_d = (double)IPT_INF;
     float dist_f = IPT_INF;
     uint32_t best = IPT_NO_HIT;
-    analytic_closest<SMALLPT>(S, o, d, dist_d, dist_f, best);
+    analytic_closest<SMALLPT, GFAST>(S, o, d, dist_d, dist_f, best);
     SurfHit r;
     r.prim = best;
     r.tri_pos = IPT_NO_HIT;
