@@ -6,6 +6,10 @@ variants = {
     "base": [],
     "next2": ["IPT_SHADE_NEXT_MIN_BLOCKS=2"],
     "next4": ["IPT_SHADE_NEXT_MIN_BLOCKS=4"],
+    "n4f4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4", "IPT_SHADE_NEXT_MIN_BLOCKS=4"],
+    "n4f3": ["IPT_SHADE_NEXT_MIN_BLOCKS=4"],
+    "n3f4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
+    "n2f2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2", "IPT_SHADE_NEXT_MIN_BLOCKS=2"],
     "fused2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2"],
     "fused3": ["IPT_SHADE_FUSED_MIN_BLOCKS=3"],
     "fused4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
