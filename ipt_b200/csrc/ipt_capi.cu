@@ -540,17 +540,17 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     s->grid_shade = occupancy_grid(k_shade<FUSE_NONE, false>, s->sm_count, 0);
     // (SmallPt scenes keep the runtime light switch; the others get the kernel compiled for their kind of light set)
     s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0)
-                          : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_LAST, false, LB_YES>, s->sm_count, 0)
-                          : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_LAST, false, LB_REF>, s->sm_count, 0)
-                          : s->inline_area_light ? occupancy_grid(k_shade<FUSE_LAST, false, LB_INLINE_AREA>, s->sm_count, 0)
-                          : dv.light_inline ? occupancy_grid(k_shade<FUSE_LAST, false, LB_INLINE>, s->sm_count, 0)
-                                            : occupancy_grid(k_shade<FUSE_LAST, false, LB_NO>, s->sm_count, 0);
+                          : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_LIGHT_BVH>, s->sm_count, 0)
+                          : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_BOX_SCENE>, s->sm_count, 0)
+                          : s->inline_area_light ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_ONE_AREA_LIGHT>, s->sm_count, 0)
+                          : dv.light_inline ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_ONE_LIGHT>, s->sm_count, 0)
+                                            : occupancy_grid(k_shade<FUSE_LAST, false, SPEC_FEW_LIGHTS>, s->sm_count, 0);
     s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0)
-                         : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_YES>, s->sm_count, 0)
-                         : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_REF>, s->sm_count, 0)
-                          : s->inline_area_light ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE_AREA>, s->sm_count, 0)
-                          : dv.light_inline ? occupancy_grid(k_shade<FUSE_NEXT, false, LB_INLINE>, s->sm_count, 0)
-                                          : occupancy_grid(k_shade<FUSE_NEXT, false, LB_NO>, s->sm_count, 0);
+                         : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_LIGHT_BVH>, s->sm_count, 0)
+                         : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_BOX_SCENE>, s->sm_count, 0)
+                          : s->inline_area_light ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_ONE_AREA_LIGHT>, s->sm_count, 0)
+                          : dv.light_inline ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_ONE_LIGHT>, s->sm_count, 0)
+                                          : occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_FEW_LIGHTS>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
         s->grid_mesh = occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
@@ -1072,21 +1072,21 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
             if (child_last && fuse_last) {
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, LB_YES><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_LAST, false, LB_REF><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_LAST, false, LB_INLINE_AREA><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, LB_INLINE><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else TIMED(2, (k_shade<FUSE_LAST, false, LB_NO><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_LIGHT_BVH><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_BOX_SCENE><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_AREA_LIGHT><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_LIGHT><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_LAST, false, SPEC_FEW_LIGHTS><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 break;
             }
             if (fuse_next && width_at[d + 1] != 0) {
                 int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, LB_YES><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_NEXT, false, LB_REF><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_NEXT, false, LB_INLINE_AREA><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, LB_INLINE><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else TIMED(2, (k_shade<FUSE_NEXT, false, LB_NO><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_LIGHT_BVH><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_BOX_SCENE><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_AREA_LIGHT><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_LIGHT><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_FEW_LIGHTS><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 traced = true; // the rays of depth d+1 are traced by this launch: no k_extend for them
                 continue;
             }

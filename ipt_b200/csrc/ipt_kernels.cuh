@@ -236,40 +236,43 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
 // nearest light, scanning in list order with strict `>` (CollectionLighting.cpp:23-34); `lpdf` receives the light part
 // of the mixture density along the same ray, sum_i w_i * DdfFromLight_i::value(d) (lighting.cpp:61-73, ddf.cpp:156-162),
 // which needs exactly the intersections this scan performs (PDF = false: nearest light only)
-// LB: whether the scene's lights sit in an LBVH — LB_RUNTIME asks the scene, LB_NO / LB_YES are the compile-time answers
-// the fused shade kernels are instantiated with (each carries only the light code its scenes run).
-// LB_INLINE: no LBVH and at most IPT_INLINE_LIGHTS lights, i.e. the constant-bank copies (every reference scene).
-// LB_INLINE_AREA: ... and that light is an area light (no sphere-light code at all).
-// LB_REF: ... and the geometry is grouped box planes + inline spheres (GFAST in ipt_trace.cuh): what every Lambert /
-// glossy box scene of the reference and of BASELINE configs[0..1] is.
-enum LightBvhMode { LB_NO = 0, LB_YES = 1, LB_RUNTIME = 2, LB_INLINE = 3, LB_INLINE_AREA = 4, LB_REF = 5 };
-#define IPT_LB_IS_INLINE(LB) ((LB) == LB_INLINE || (LB) == LB_INLINE_AREA || (LB) == LB_REF)
-#define IPT_LB_IS_AREA(LB) ((LB) == LB_INLINE_AREA || (LB) == LB_REF)
-template <int LB>
-__device__ __forceinline__ bool has_light_bvh(const DevScene& S) { return LB == LB_RUNTIME ? S.n_light_bvh != 0 : LB == LB_YES; }
-template <int LB>
-__device__ __forceinline__ bool lights_inline(const DevScene& S) { return IPT_LB_IS_INLINE(LB) ? true : LB == LB_YES ? false : S.light_inline != 0; }
-template <int LB>
+// SPEC: what the fused shade kernels know about the scene at COMPILE time, so that each instantiation carries only the
+// light and geometry code its scenes can run (the generic kernel was 10 360 SASS instructions, the box-scene one is 2944):
+//   SPEC_RUNTIME          nothing: every decision is taken from the scene (k_extend, the mesh path, SmallPt scenes)
+//   SPEC_LIGHT_BVH        the lights sit in the light LBVH (> 8 lights)
+//   SPEC_FEW_LIGHTS       no LBVH; inline or linear scan decided at run time
+//   SPEC_ONE_LIGHT        no LBVH and at most IPT_INLINE_LIGHTS lights, i.e. the constant-bank copies
+//   SPEC_ONE_AREA_LIGHT   ... and that light is an area light (no sphere-light code at all)
+//   SPEC_BOX_SCENE        ... and the geometry is grouped box planes + inline spheres (GFAST in ipt_trace.cuh): every
+//                         Lambert / glossy box scene of the reference and BASELINE configs[0..1]
+enum SceneSpec { SPEC_FEW_LIGHTS = 0, SPEC_LIGHT_BVH = 1, SPEC_RUNTIME = 2, SPEC_ONE_LIGHT = 3, SPEC_ONE_AREA_LIGHT = 4, SPEC_BOX_SCENE = 5 };
+#define IPT_SPEC_INLINE_LIGHTS(SPEC) ((SPEC) == SPEC_ONE_LIGHT || (SPEC) == SPEC_ONE_AREA_LIGHT || (SPEC) == SPEC_BOX_SCENE)
+#define IPT_SPEC_AREA_LIGHTS(SPEC) ((SPEC) == SPEC_ONE_AREA_LIGHT || (SPEC) == SPEC_BOX_SCENE)
+template <int SPEC>
+__device__ __forceinline__ bool has_light_bvh(const DevScene& S) { return SPEC == SPEC_RUNTIME ? S.n_light_bvh != 0 : SPEC == SPEC_LIGHT_BVH; }
+template <int SPEC>
+__device__ __forceinline__ bool lights_inline(const DevScene& S) { return IPT_SPEC_INLINE_LIGHTS(SPEC) ? true : SPEC == SPEC_LIGHT_BVH ? false : S.light_inline != 0; }
+template <int SPEC>
 __device__ __forceinline__ float light_power(const DevScene& S, uint32_t i) {
-    float power = lights_inline<LB>(S) ? S.lights[i].surface_power : S.lights_g[i].surface_power;
+    float power = lights_inline<SPEC>(S) ? S.lights[i].surface_power : S.lights_g[i].surface_power;
     return isfinite(power) ? power : 1.0f; // main.cpp:123 point-light hack
 }
-template <bool PDF = true, int LB = LB_RUNTIME>
+template <bool PDF = true, int SPEC = SPEC_RUNTIME>
 __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& lpdf) {
     bool any = false;
     float best_len = 0.0f;
     lpdf = 0.0f;
-    if (has_light_bvh<LB>(S)) {
+    if (has_light_bvh<SPEC>(S)) {
         if (PDF) lpdf = light_bvh_query<LQ_BOTH>(S, o, d, which, lpos);
         else light_bvh_query<LQ_NEAREST>(S, o, d, which, lpos);
         return which != IPT_NO_HIT;
     }
-    if (LB == LB_YES) return false; // unreachable: the LBVH branch above always returns
-    if (lights_inline<LB>(S)) {
+    if (SPEC == SPEC_LIGHT_BVH) return false; // unreachable: the LBVH branch above always returns
+    if (lights_inline<SPEC>(S)) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
-            if (i < (int)S.n_lights) trace_one_light<PDF, IPT_LB_IS_AREA(LB)>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
-    } else if (!IPT_LB_IS_INLINE(LB)) {
+            if (i < (int)S.n_lights) trace_one_light<PDF, IPT_SPEC_AREA_LIGHTS(SPEC)>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
+    } else if (!IPT_SPEC_INLINE_LIGHTS(SPEC)) {
         for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light<PDF>(S.lights_g[i], i, o, d, any, best_len, which, lpos, lpdf);
     }
     return any;
@@ -284,13 +287,13 @@ struct Outcome {
 };
 
 // Geometry::traceRay + Lighting::traceRayToLight + the decision of main.cpp:111-128
-template <bool SMALLPT, bool MESH, int LB = LB_RUNTIME>
+template <bool SMALLPT, bool MESH, int SPEC = SPEC_RUNTIME>
 __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
-    r.surf = trace_geometry<SMALLPT, MESH, LB == LB_REF>(S, o, d, tc);
+    r.surf = trace_geometry<SMALLPT, MESH, SPEC == SPEC_BOX_SCENE>(S, o, d, tc);
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
-    bool lh = trace_lights<true, LB>(S, o, d, r.light, r.light_pos, r.light_pdf);
+    bool lh = trace_lights<true, SPEC>(S, o, d, r.light, r.light_pos, r.light_pdf);
     bool sh = r.surf.prim != IPT_NO_HIT;
     r.kind = 0;
     if (lh) {
@@ -309,16 +312,16 @@ __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, Tr
 // a light before any surface. Lights are tested first and the geometry only for rays that hit one ("shadow ray"):
 // the decision is the same expression as in trace_scene, evaluated for fewer rays. kind 3 = no light along the ray
 // (surface or miss, not resolved).
-template <bool SMALLPT, bool MESH, int LB = LB_RUNTIME>
+template <bool SMALLPT, bool MESH, int SPEC = SPEC_RUNTIME>
 __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
     r.surf.prim = IPT_NO_HIT; r.surf.t = IPT_INF; r.surf.tri_pos = IPT_NO_HIT;
-    bool lh = trace_lights<true, LB>(S, o, d, r.light, r.light_pos, r.light_pdf);
+    bool lh = trace_lights<true, SPEC>(S, o, d, r.light, r.light_pos, r.light_pdf);
     r.kind = 3;
     if (!lh) return r;
-    r.surf = trace_geometry<SMALLPT, MESH, LB == LB_REF>(S, o, d, tc);
+    r.surf = trace_geometry<SMALLPT, MESH, SPEC == SPEC_BOX_SCENE>(S, o, d, tc);
     bool sh = r.surf.prim != IPT_NO_HIT;
     bool light_wins = !sh;
     if (sh) {
@@ -441,13 +444,13 @@ __device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, 
 #endif
 // Second half of trace_scene_last for a parked ray that reached a light at `lpos`: Geometry::traceRay and the
 // light-vs-surface decision of main.cpp:113; the light's contribution is added if nothing is nearer.
-template <bool SMALLPT, int LB>
+template <bool SMALLPT, int SPEC>
 __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, TraceCounters& tc,
                                                uint32_t& n_light, uint32_t& n_surface) {
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
     f3 lpos = mk3(dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], dq[8 * IPT_PARK + k]);
-    SurfHit sh = trace_geometry<SMALLPT, false, LB == LB_REF>(S, o, d, tc);
+    SurfHit sh = trace_geometry<SMALLPT, false, SPEC == SPEC_BOX_SCENE>(S, o, d, tc);
     bool light_wins = sh.prim == IPT_NO_HIT;
     if (!light_wins) {
         f3 sp = xpoint(o, d, sh.t);
@@ -474,7 +477,7 @@ __device__ __forceinline__ void last_parked(const DevScene& S, const RenderCtx& 
                                             uint32_t& n_light, uint32_t& n_surface, uint32_t& n_dropped) {
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
-    Outcome oc = trace_scene_last<SMALLPT, false, LB_YES>(S, o, d, tc);
+    Outcome oc = trace_scene_last<SMALLPT, false, SPEC_LIGHT_BVH>(S, o, d, tc);
     float wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
     if (!isfinite(wr)) ++n_dropped;
     else if (oc.kind == 2) {
@@ -491,7 +494,7 @@ struct ExtendCounters {
 // The body of k_extend<.., LAST = false> for one parked child ray of depth `depth` (entry k of the warp's queue; all 32
 // lanes call this, `valid` masks the drain): trace_scene, weight resolution, emission, and the warp-aggregated append
 // of the surface hits to the hit set of `depth`.
-template <bool SMALLPT, int LB>
+template <bool SMALLPT, int SPEC>
 __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, bool valid, uint32_t depth,
                                               TraceCounters& tc, ExtendCounters& ec) {
     const uint32_t lane = threadIdx.x & 31;
@@ -504,12 +507,12 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
         o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
         d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
         ctag = __float_as_uint(dq[8 * IPT_PARK + k]);
-        oc = trace_scene<SMALLPT, false, LB>(S, o, d, tc);
+        oc = trace_scene<SMALLPT, false, SPEC>(S, o, d, tc);
         wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
         if (!isfinite(wr)) ++ec.dropped; // non-finite multiplier (main.cpp:175): drop this sample
         else if (oc.kind == 2) {
             ++ec.light;
-            atomicAdd(&C.pathval[ctag & C.slot_mask], wr * light_power<LB>(S, oc.light));
+            atomicAdd(&C.pathval[ctag & C.slot_mask], wr * light_power<SPEC>(S, oc.light));
         } else if (oc.kind == 1) {
             ++ec.surface;
             emit = true;
@@ -540,7 +543,7 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
 //              light test at once, and only the rays that reach a light are parked for the occlusion test.
 // Same functions, same operands, same counters as the separate kernels.
 enum ShadeFusion { FUSE_NONE = 0, FUSE_NEXT = 1, FUSE_LAST = 2 };
-template <int FUSE, bool SMALLPT, int LB = LB_RUNTIME>
+template <int FUSE, bool SMALLPT, int SPEC = SPEC_RUNTIME>
 __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_BLOCKS : FUSE == FUSE_NEXT ? IPT_SHADE_NEXT_MIN_BLOCKS : IPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth + 1];
     const uint32_t lane = threadIdx.x & 31;
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
-                w = mix_sample<IPT_LB_IS_INLINE(LB), IPT_LB_IS_AREA(LB)>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                w = mix_sample<IPT_SPEC_INLINE_LIGHTS(SPEC), IPT_SPEC_AREA_LIGHTS(SPEC)>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
                     if (FUSE == FUSE_NONE && (C.flags & 4u)) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     __syncwarp();
                     if (qn >= 32) {
                         qn -= 32;
-                        extend_parked<SMALLPT, LB>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
+                        extend_parked<SMALLPT, SPEC>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
                         __syncwarp();
                     }
                 }
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                 // the body of k_extend<LAST> for this ray, in two steps: the light test now; the occlusion test of the
                 // rays that did reach a light (about a third) is parked in a per-warp shared-memory queue and run 32 at a
                 // time, so the geometry intersection is issued for full warps instead of for the third of the lanes
-                if (has_light_bvh<LB>(S)) {
+                if (has_light_bvh<SPEC>(S)) {
                     // many lights: regroup BEFORE the light-LBVH walk. A ray that misses the root boxes sees no light and,
                     // at the last traced depth, is done; the others are parked and walk the LBVH 32 at a time.
                     bool parkb = false;
@@ -671,11 +674,11 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     ++n_fused;
                     uint32_t li = IPT_NO_HIT;
                     float lpdf;
-                    bool lh = trace_lights<true, LB == LB_YES ? LB_NO : LB>(S, pos, w, li, lpos, lpdf);
+                    bool lh = trace_lights<true, SPEC == SPEC_LIGHT_BVH ? SPEC_FEW_LIGHTS : SPEC>(S, pos, w, li, lpos, lpdf);
                     float wr = resolve_weight(S, wgt, child_sv, lpdf);
                     if (!isfinite(wr)) ++n_dropped;
                     else if (lh) {
-                        contrib = wr * light_power<LB>(S, li);
+                        contrib = wr * light_power<SPEC>(S, li);
                         park = true;
                     }
                 }
@@ -692,7 +695,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     __syncwarp();
                     if (qn >= 32) {
                         qn -= 32;
-                        resolve_parked<SMALLPT, LB>(S, C, dq, qn + lane, tc, n_light, n_surface);
+                        resolve_parked<SMALLPT, SPEC>(S, C, dq, qn + lane, tc, n_light, n_surface);
                         __syncwarp();
                     }
                 }
@@ -715,10 +718,10 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
         }
     }
     if (FUSE == FUSE_LAST && lane < qn) { // drain
-        if (has_light_bvh<LB>(S)) last_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
-        else resolve_parked<SMALLPT, LB>(S, C, dq, lane, tc, n_light, n_surface);
+        if (has_light_bvh<SPEC>(S)) last_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
+        else resolve_parked<SMALLPT, SPEC>(S, C, dq, lane, tc, n_light, n_surface);
     }
-    if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT, LB>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
+    if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT, SPEC>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
     n_light += ec.light; n_surface += ec.surface; n_dropped += ec.dropped;
     flush_stat(C.stats, ST_FAILED, n_failed);
     flush_stat(C.stats, ST_PRUNED, n_pruned);
