@@ -101,6 +101,7 @@ struct ipt_scene {
     bool smallpt = false, mesh = false;
     bool inline_area_light = false; // the scene's lights are the inline ones and all of them are area lights
     bool geom_fast = false;         // grouped box planes + inline spheres only (analytic_closest's first branch)
+    bool mesh_box_scene = false;    // mesh scene whose lights / analytic primitives allow k_extend_mesh<.., SPEC_BOX_SCENE>
     Workspace ws;
     uint32_t* d_cnt = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -553,8 +554,9 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
                                           : occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_FEW_LIGHTS>, s->sm_count, 0);
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
-        s->grid_mesh = occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
-        s->grid_mesh_last = occupancy_grid(k_extend_mesh<true>, s->sm_count, sm);
+        s->mesh_box_scene = s->inline_area_light && dv.planes_grouped && dv.others_inline;
+        s->grid_mesh = s->mesh_box_scene ? occupancy_grid(k_extend_mesh<false, SPEC_BOX_SCENE>, s->sm_count, sm) : occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
+        s->grid_mesh_last = s->mesh_box_scene ? occupancy_grid(k_extend_mesh<true, SPEC_BOX_SCENE>, s->sm_count, sm) : occupancy_grid(k_extend_mesh<true>, s->sm_count, sm);
     }
 #define OCC(SP, MS)                                                                          \
     s->grid_extend = occupancy_grid(k_extend<SP, MS, false>, s->sm_count, sm);               \
@@ -1044,10 +1046,12 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
             if (persistent_mesh) {
                 // mesh scenes: persistent warps that refill idle lanes from the ray queue (ipt_trace.cuh)
                 if (last) {
-                    TIMED(1, (k_extend_mesh<true><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                    if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<true, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                    else TIMED(1, (k_extend_mesh<true><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
                     break;
                 }
-                TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<false, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                else TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
                 int gs2 = std::max(1, std::min(s->grid_shade, cap_blocks));
                 TIMED(2, (k_shade<FUSE_NONE, false><<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 continue;

@@ -191,7 +191,10 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 #ifndef IPT_MESH_MIN_BLOCKS
 #define IPT_MESH_MIN_BLOCKS 4
 #endif
-template <bool LAST>
+// SPEC (see SceneSpec in ipt_kernels.cuh): SPEC_BOX_SCENE = one inline area light, analytic part = grouped box planes +
+// inline spheres — the kernel then carries no light-LBVH walk (and not its 64-entry local stack), no sphere-light code
+// and none of the generic primitive scans; SPEC_RUNTIME decides everything from the scene.
+template <bool LAST, int SPEC = SPEC_RUNTIME>
 __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth];
     uint32_t* next = &C.fetch[depth];
@@ -225,10 +228,10 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                 if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) { // shadow ray: nothing to do unless a light lies along it
                     lwhich = IPT_NO_HIT;
                     float lpdf;
-                    if (S.light_inline) {
-                        go = trace_lights<false>(S, o, d, lwhich, lpos, lpdf); // density from lpos when the ray is finalised
+                    if (lights_inline<SPEC>(S)) {
+                        go = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf); // density from lpos when the ray is finalised
                     } else {
-                        go = trace_lights(S, o, d, lwhich, lpos, lpdf);
+                        go = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf);
                         ro.w = resolve_weight(S, ro.w, sv, lpdf); // resolved now: no density register lives through the traversal
                         sv = -1.0f;
                     }
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                 if (go) {
                     double dd = (double)IPT_INF;
                     a_t = IPT_INF; a_prim = IPT_NO_HIT;
-                    analytic_closest<false>(S, o, d, dd, a_t, a_prim);
+                    analytic_closest<false, SPEC == SPEC_BOX_SCENE>(S, o, d, dd, a_t, a_prim);
                     best_t = a_t; best_orig = IPT_NO_HIT; best_pos = IPT_NO_HIT;
                     have = true;
                     if (S.n_tris == 1) {
@@ -317,11 +320,11 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
             if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) lh = true;
             else {
                 lwhich = IPT_NO_HIT;
-                if (S.light_inline) lh = trace_lights<false>(S, o, d, lwhich, lpos, lpdf);
-                else lh = trace_lights(S, o, d, lwhich, lpos, lpdf);
+                if (lights_inline<SPEC>(S)) lh = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf);
+                else lh = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf);
             }
             // single inline light: its density follows from the hit position that is kept anyway
-            if (S.light_inline && lh && S.n_lights) lpdf = S.lights[0].weight * light_pdf_at(S.lights[0], o, lpos);
+            if (lights_inline<SPEC>(S) && lh && S.n_lights) lpdf = S.lights[0].weight * light_pdf_at<IPT_SPEC_AREA_LIGHTS(SPEC)>(S.lights[0], o, lpos);
             bool sh = prim != IPT_NO_HIT;
             float K = ro.w;
             ro.w = resolve_weight(S, ro.w, sv, lpdf);
@@ -339,8 +342,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                 }
                 if (light_wins) {
                     ++n_light;
-                    float power = S.light_inline ? S.lights[lwhich].surface_power : S.lights_g[lwhich].surface_power;
-                    if (!isfinite(power)) power = 1.0f;
+                    float power = light_power<SPEC>(S, lwhich);
                     atomicAdd(&C.pathval[__float_as_uint(rd.w) & C.slot_mask], ro.w * power);
                 } else if (sh) {
                     ++n_surface;
