@@ -30,6 +30,35 @@ def test_struct_layouts_match_the_header(lib):
     assert (p.width, p.height, p.depth_max, list(p.schedule)[:4], p.plane_mode) == (640, 640, 4, [16, 8, 4, 2], capi.PLANE_GRID)
 
 
+def test_enum_values_and_struct_sizes_against_a_c_compiler(lib, tmp_path):
+    """The numeric constants and struct sizes of the ctypes mirror against what gcc sees in include/ipt_b200.h."""
+    import subprocess
+
+    names = ["IPT_FLAG_TIME_KERNELS", "IPT_FLAG_KEEP_ZERO_WEIGHT", "IPT_FLAG_DEBUG_PRINT", "IPT_FLAG_RESOLVE_LAST_LEVEL",
+             "IPT_FLAG_NO_FUSED_LAST_LEVEL", "IPT_FLAG_NO_FUSED_TRACE", "IPT_PLANE_GRID", "IPT_PLANE_GUI", "IPT_PLANE_LINEAR",
+             "IPT_KEY_LEFT", "IPT_KEY_RIGHT", "IPT_KEY_DOWN", "IPT_KEY_UP", "IPT_ERR_INVALID", "IPT_ERR_NO_DEVICE", "IPT_MAX_DEPTH"]
+    structs = ["ipt_material", "ipt_prim", "ipt_light", "ipt_camera", "ipt_scene_desc", "ipt_render_params", "ipt_render_stats", "ipt_bvh_node"]
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include "ipt_b200.h"\nint main(void) {\n'
+                   + "".join(f'  printf("{n} %lld\\n", (long long){n});\n' for n in names)
+                   + "".join(f'  printf("sizeof_{t} %zu\\n", sizeof({t}));\n' for t in structs) + "  return 0;\n}\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", f"-I{ROOT / 'include'}", "-o", str(exe), str(src)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    got = {k: int(v) for k, v in got.items()}
+    want = {"IPT_FLAG_TIME_KERNELS": capi.FLAG_TIME_KERNELS, "IPT_FLAG_KEEP_ZERO_WEIGHT": capi.FLAG_KEEP_ZERO_WEIGHT,
+            "IPT_FLAG_DEBUG_PRINT": capi.FLAG_DEBUG_PRINT, "IPT_FLAG_RESOLVE_LAST_LEVEL": capi.FLAG_RESOLVE_LAST_LEVEL,
+            "IPT_FLAG_NO_FUSED_LAST_LEVEL": capi.FLAG_NO_FUSED_LAST_LEVEL, "IPT_FLAG_NO_FUSED_TRACE": capi.FLAG_NO_FUSED_TRACE,
+            "IPT_PLANE_GRID": capi.PLANE_GRID, "IPT_PLANE_GUI": capi.PLANE_GUI, "IPT_PLANE_LINEAR": capi.PLANE_LINEAR,
+            "IPT_KEY_LEFT": 0, "IPT_KEY_RIGHT": 1, "IPT_KEY_DOWN": 2, "IPT_KEY_UP": 3,
+            "IPT_ERR_INVALID": capi.IPT_ERR_INVALID, "IPT_ERR_NO_DEVICE": capi.IPT_ERR_NO_DEVICE, "IPT_MAX_DEPTH": capi.IPT_MAX_DEPTH,
+            "sizeof_ipt_material": C.sizeof(capi.Material), "sizeof_ipt_prim": C.sizeof(capi.Prim), "sizeof_ipt_light": C.sizeof(capi.Light),
+            "sizeof_ipt_camera": C.sizeof(capi.Camera), "sizeof_ipt_scene_desc": C.sizeof(capi.SceneDesc),
+            "sizeof_ipt_render_params": C.sizeof(capi.RenderParams), "sizeof_ipt_render_stats": C.sizeof(capi.RenderStats),
+            "sizeof_ipt_bvh_node": C.sizeof(capi.BvhNode)}
+    assert got == want
+
+
 def test_no_cpu_fallback(lib, has_gpu):
     """Without a CUDA device every compute entry point fails loudly with IPT_ERR_NO_DEVICE."""
     if has_gpu:
