@@ -95,6 +95,12 @@ __device__ __forceinline__ float base_value(int kind, float z) {
     return ((float)kind + 1.0f) * ipow(z, kind) * (0.5f / IPT_PI_F);
 }
 
+#ifndef IPT_LOBE_LOG2
+// log2 inside cos^n of the glossy lobe: the SFU's __log2f (abs. error 2^-21.4 on [0.5, 2]) puts at most 1e-5 of relative
+// error on cos^40 at the lobe's peak — statistical domain (downstream of a random direction), and the per-pixel parity
+// tests against the oracle's powf hold unchanged; log2f costs 4 % of the fused kernels' instructions (C2 292 vs 300).
+#define IPT_LOBE_LOG2 __log2f
+#endif
 // The surface DDF of a hit: RotateDdf(CosineDdf, normal) or the glossy extension. Both are members of one family —
 // kd * PowerCosine(1) about the normal + ks * PowerCosine(n) about the mirror direction, with kd = 1, ks = 0 for the
 // Lambert case — and are evaluated by ONE branch-free code path: hits of both materials share warps at every depth
@@ -128,7 +134,7 @@ __device__ __forceinline__ Sdf make_sdf(const DevMaterial& m, f3 normal, f3 dir_
 __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
     float cn = dot3(s.normal, w);
     float zr = dot3(s.refl, w);
-    float lobe = zr > 0.0f ? exp2f(pmul(s.exponent, log2f(zr))) : 0.0f;
+    float lobe = zr > 0.0f ? exp2f(pmul(s.exponent, IPT_LOBE_LOG2(zr))) : 0.0f;
     float v = pfma(s.ws, pmul(s.lobe_norm, lobe), pmul(s.wd, pmul(cn, 1.0f / IPT_PI_F)));
     return cn < 0.0f ? 0.0f : v;
 }
