@@ -2,23 +2,13 @@
 import json, os, subprocess, sys
 sys.path.insert(0, '.')
 from ipt_b200 import build
-variants = {
+variants = {  # -D flags of ipt_b200/csrc; the adopted values are the defaults in the sources (profiles/tuning_r01.md)
     "base": [],
-    "next2": ["IPT_SHADE_NEXT_MIN_BLOCKS=2"],
-    "next4": ["IPT_SHADE_NEXT_MIN_BLOCKS=4"],
-    "n4f4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4", "IPT_SHADE_NEXT_MIN_BLOCKS=4"],
-    "n4f3": ["IPT_SHADE_NEXT_MIN_BLOCKS=4"],
-    "n3f4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
-    "n2f2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2", "IPT_SHADE_NEXT_MIN_BLOCKS=2"],
-    "fused2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2"],
-    "fused3": ["IPT_SHADE_FUSED_MIN_BLOCKS=3"],
-    "fused4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
-    "fused3_ext4": ["IPT_SHADE_FUSED_MIN_BLOCKS=3", "IPT_EXTEND_MIN_BLOCKS=4"],
-    "fused3_shade3": ["IPT_SHADE_FUSED_MIN_BLOCKS=3", "IPT_SHADE_MIN_BLOCKS=3"],
-    "lights4": ["IPT_INLINE_LIGHTS=4"],
-    "shade3": ["IPT_SHADE_MIN_BLOCKS=3"],
-    "ext2": ["IPT_EXTEND_MIN_BLOCKS=2"],
-    "ext4": ["IPT_EXTEND_MIN_BLOCKS=4"],
+    "fused2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2"], "fused4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4"],
+    "next2": ["IPT_SHADE_NEXT_MIN_BLOCKS=2"], "next4": ["IPT_SHADE_NEXT_MIN_BLOCKS=4"],
+    "n4f4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4", "IPT_SHADE_NEXT_MIN_BLOCKS=4"], "n2f2": ["IPT_SHADE_FUSED_MIN_BLOCKS=2", "IPT_SHADE_NEXT_MIN_BLOCKS=2"],
+    "shade3": ["IPT_SHADE_MIN_BLOCKS=3"], "ext2": ["IPT_EXTEND_MIN_BLOCKS=2"], "ext4": ["IPT_EXTEND_MIN_BLOCKS=4"],
+    "lights4": ["IPT_INLINE_LIGHTS=4"], "accurate_log2": ["IPT_LOBE_LOG2=log2f"],
 }
 sel = sys.argv[1].split(",") if len(sys.argv) > 1 else list(variants)
 batches = [int(b) for b in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0"])]
