@@ -101,6 +101,7 @@ struct ipt_scene {
     bool smallpt = false, mesh = false;
     bool inline_area_light = false; // the scene's lights are the inline ones and all of them are area lights
     bool geom_fast = false;         // grouped box planes + inline spheres only (analytic_closest's first branch)
+    bool all_lambert = false;       // every material is the cosine DDF
     bool mesh_box_scene = false;    // mesh scene whose lights / analytic primitives allow k_extend_mesh<.., SPEC_BOX_SCENE>
     Workspace ws;
     uint32_t* d_cnt = nullptr;
@@ -496,6 +497,8 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     s->smallpt = smallpt;
     s->mesh = desc->n_triangles > 0;
     s->geom_fast = !smallpt && !s->mesh && dv.planes_grouped && dv.others_inline;
+    s->all_lambert = true;
+    for (const DevMaterial& m : mats) if (m.ddf != IPT_DDF_COSINE) s->all_lambert = false;
     if (s->mesh) {
         std::string err;
         if (lbvh_build(desc->triangles, (uint32_t)desc->n_triangles, s->stream, s->bvh, err) != 0) {
@@ -542,13 +545,15 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     // (SmallPt scenes keep the runtime light switch; the others get the kernel compiled for their kind of light set)
     s->grid_shade_fused = s->smallpt ? occupancy_grid(k_shade<FUSE_LAST, true>, s->sm_count, 0)
                           : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_LIGHT_BVH>, s->sm_count, 0)
+                          : (s->inline_area_light && s->geom_fast && s->all_lambert) ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_LAMBERT_BOX>, s->sm_count, 0)
                           : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_BOX_SCENE>, s->sm_count, 0)
                           : s->inline_area_light ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_ONE_AREA_LIGHT>, s->sm_count, 0)
                           : dv.light_inline ? occupancy_grid(k_shade<FUSE_LAST, false, SPEC_ONE_LIGHT>, s->sm_count, 0)
                                             : occupancy_grid(k_shade<FUSE_LAST, false, SPEC_FEW_LIGHTS>, s->sm_count, 0);
     s->grid_shade_next = s->smallpt ? occupancy_grid(k_shade<FUSE_NEXT, true>, s->sm_count, 0)
                          : dv.n_light_bvh ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_LIGHT_BVH>, s->sm_count, 0)
-                         : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_BOX_SCENE>, s->sm_count, 0)
+                         : (s->inline_area_light && s->geom_fast && s->all_lambert) ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_LAMBERT_BOX>, s->sm_count, 0)
+                          : (s->inline_area_light && s->geom_fast) ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_BOX_SCENE>, s->sm_count, 0)
                           : s->inline_area_light ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_ONE_AREA_LIGHT>, s->sm_count, 0)
                           : dv.light_inline ? occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_ONE_LIGHT>, s->sm_count, 0)
                                           : occupancy_grid(k_shade<FUSE_NEXT, false, SPEC_FEW_LIGHTS>, s->sm_count, 0);
@@ -1077,6 +1082,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_LIGHT_BVH><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast && s->all_lambert) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_LAMBERT_BOX><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_BOX_SCENE><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_AREA_LIGHT><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_LIGHT><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
@@ -1087,6 +1093,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
                 if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_LIGHT_BVH><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast && s->all_lambert) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_LAMBERT_BOX><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_BOX_SCENE><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_AREA_LIGHT><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_LIGHT><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));

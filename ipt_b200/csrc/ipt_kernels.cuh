@@ -245,9 +245,11 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
 //   SPEC_ONE_AREA_LIGHT   ... and that light is an area light (no sphere-light code at all)
 //   SPEC_BOX_SCENE        ... and the geometry is grouped box planes + inline spheres (GFAST in ipt_trace.cuh): every
 //                         Lambert / glossy box scene of the reference and BASELINE configs[0..1]
-enum SceneSpec { SPEC_FEW_LIGHTS = 0, SPEC_LIGHT_BVH = 1, SPEC_RUNTIME = 2, SPEC_ONE_LIGHT = 3, SPEC_ONE_AREA_LIGHT = 4, SPEC_BOX_SCENE = 5 };
-#define IPT_SPEC_INLINE_LIGHTS(SPEC) ((SPEC) == SPEC_ONE_LIGHT || (SPEC) == SPEC_ONE_AREA_LIGHT || (SPEC) == SPEC_BOX_SCENE)
-#define IPT_SPEC_AREA_LIGHTS(SPEC) ((SPEC) == SPEC_ONE_AREA_LIGHT || (SPEC) == SPEC_BOX_SCENE)
+//   SPEC_LAMBERT_BOX      ... and every material is the cosine DDF (the reference's own box scenes, BASELINE configs[0])
+enum SceneSpec { SPEC_FEW_LIGHTS = 0, SPEC_LIGHT_BVH = 1, SPEC_RUNTIME = 2, SPEC_ONE_LIGHT = 3, SPEC_ONE_AREA_LIGHT = 4, SPEC_BOX_SCENE = 5, SPEC_LAMBERT_BOX = 6 };
+#define IPT_SPEC_INLINE_LIGHTS(SPEC) ((SPEC) == SPEC_ONE_LIGHT || (SPEC) == SPEC_ONE_AREA_LIGHT || (SPEC) == SPEC_BOX_SCENE || (SPEC) == SPEC_LAMBERT_BOX)
+#define IPT_SPEC_AREA_LIGHTS(SPEC) ((SPEC) == SPEC_ONE_AREA_LIGHT || (SPEC) == SPEC_BOX_SCENE || (SPEC) == SPEC_LAMBERT_BOX)
+#define IPT_SPEC_FAST_GEOMETRY(SPEC) ((SPEC) == SPEC_BOX_SCENE || (SPEC) == SPEC_LAMBERT_BOX)
 template <int SPEC>
 __device__ __forceinline__ bool has_light_bvh(const DevScene& S) { return SPEC == SPEC_RUNTIME ? S.n_light_bvh != 0 : SPEC == SPEC_LIGHT_BVH; }
 template <int SPEC>
@@ -290,7 +292,7 @@ struct Outcome {
 template <bool SMALLPT, bool MESH, int SPEC = SPEC_RUNTIME>
 __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
-    r.surf = trace_geometry<SMALLPT, MESH, SPEC == SPEC_BOX_SCENE>(S, o, d, tc);
+    r.surf = trace_geometry<SMALLPT, MESH, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, tc);
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
     bool lh = trace_lights<true, SPEC>(S, o, d, r.light, r.light_pos, r.light_pdf);
@@ -321,7 +323,7 @@ __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 
     bool lh = trace_lights<true, SPEC>(S, o, d, r.light, r.light_pos, r.light_pdf);
     r.kind = 3;
     if (!lh) return r;
-    r.surf = trace_geometry<SMALLPT, MESH, SPEC == SPEC_BOX_SCENE>(S, o, d, tc);
+    r.surf = trace_geometry<SMALLPT, MESH, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, tc);
     bool sh = r.surf.prim != IPT_NO_HIT;
     bool light_wins = !sh;
     if (sh) {
@@ -450,7 +452,7 @@ __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCt
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
     f3 lpos = mk3(dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], dq[8 * IPT_PARK + k]);
-    SurfHit sh = trace_geometry<SMALLPT, false, SPEC == SPEC_BOX_SCENE>(S, o, d, tc);
+    SurfHit sh = trace_geometry<SMALLPT, false, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, tc);
     bool light_wins = sh.prim == IPT_NO_HIT;
     if (!light_wins) {
         f3 sp = xpoint(o, d, sh.t);
@@ -588,10 +590,10 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             m.ddf = __float_as_uint(m0.x); m.albedo = m0.y; m.wd = m0.z; m.ws = m0.w; m.exponent = m1.x;
             albedo = m.albedo;
             f3 din = mk3(0, 0, 0);
-            if (m.ddf == IPT_DDF_GLOSSY) din = oct_decode(__uint_as_float(b.z), __uint_as_float(b.w)); // only the glossy lobe needs it
+            if (SPEC != SPEC_LAMBERT_BOX && m.ddf == IPT_DDF_GLOSSY) din = oct_decode(__uint_as_float(b.z), __uint_as_float(b.w)); // only the glossy lobe needs it
             sdf = make_sdf(m, normal, din);
             bn = make_basis(normal);
-            bl = m.ddf == IPT_DDF_GLOSSY ? make_basis(sdf.refl) : bn;
+            bl = (SPEC != SPEC_LAMBERT_BOX && m.ddf == IPT_DDF_GLOSSY) ? make_basis(sdf.refl) : bn;
         }
         for (uint32_t c = 0; c < n_children; ++c) {
             bool emit = false;
@@ -600,12 +602,12 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
-                w = mix_sample<IPT_SPEC_INLINE_LIGHTS(SPEC), IPT_SPEC_AREA_LIGHTS(SPEC)>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                w = mix_sample<IPT_SPEC_INLINE_LIGHTS(SPEC), IPT_SPEC_AREA_LIGHTS(SPEC), SPEC == SPEC_LAMBERT_BOX>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
                     if (FUSE == FUSE_NONE && (C.flags & 4u)) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
                 } else {
-                    float sv = sdf_value(sdf, w);
+                    float sv = sdf_value<SPEC == SPEC_LAMBERT_BOX>(sdf, w);
                     // the ray's own light intersection (k_extend, or the fused block below) also yields the light part of
                     // the mixture density, so the weight K*sv/mix is resolved there; sv == 0 already means weight 0
                     wgt = pmul(pmul(thr, albedo), inv_n);

@@ -131,8 +131,11 @@ __device__ __forceinline__ Sdf make_sdf(const DevMaterial& m, f3 normal, f3 dir_
     return s;
 }
 // Lambert: z/pi (ddf.cpp:104-108); glossy: kd*z/pi + ks*(n+1)/(2 pi)*cos^n about the mirror direction, 0 below the surface
+// LAMBERT: the caller knows at compile time that every material of the scene is the cosine DDF
+template <bool LAMBERT = false>
 __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
     float cn = dot3(s.normal, w);
+    if (LAMBERT) return cn < 0.0f ? 0.0f : pmul(cn, 1.0f / IPT_PI_F); // == the general expression with kd = 1, ks = 0
     float zr = dot3(s.refl, w);
     float lobe = zr > 0.0f ? exp2f(pmul(s.exponent, IPT_LOBE_LOG2(zr))) : 0.0f;
     float v = pfma(s.ws, pmul(s.lobe_norm, lobe), pmul(s.wd, pmul(cn, 1.0f / IPT_PI_F)));
@@ -140,8 +143,9 @@ __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
 }
 // zero vector == failed sample. ul is the lobe-selection draw (ROLE_LOBE in the oracle).
 // bl: basis about the mirror direction (== bn for Lambert hits; built once per hit, not per child)
+template <bool LAMBERT = false>
 __device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, const Basis& bl, float u1, float u2, float ul) {
-    bool lobe = !(ul < s.wd);               // never for Lambert (wd = 1 > ul)
+    bool lobe = !LAMBERT && !(ul < s.wd);   // never for Lambert (wd = 1 > ul)
     float e = lobe ? s.inv_np1 : 0.5f;      // cos(alpha) = u1^(1/(n+1)); sqrt(u1) for the cosine DDF (ddf.cpp:94)
     float zc = exp2f(pmul(__log2f(u1), e)); // u1 = 0 -> 0
     float r = fsqrt(fmaxf(0.0f, pfma(-zc, zc, 1.0f)));
@@ -153,7 +157,7 @@ __device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, const Ba
     b.c1 = lobe ? bl.c1 : bn.c1;
     b.c2 = lobe ? bl.c2 : bn.c2;
     f3 w = rotate(b, x);
-    bool below = s.ddf == IPT_DDF_GLOSSY && dot3(s.normal, w) < 0.0f;
+    bool below = !LAMBERT && s.ddf == IPT_DDF_GLOSSY && dot3(s.normal, w) < 0.0f;
     return below ? mk3(0, 0, 0) : w;
 }
 
@@ -246,7 +250,7 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
 // component whose running sum exceeds it is sampled. r >= total (float rounding; uninitialised result in the
 // reference) is a failed sample. Both candidate directions are formed by every lane (no light-vs-sdf divergence).
 // INLINE_LIGHTS: 1 = the caller knows the lights are the inline ones (compile-time), 0 = ask the scene; AREA: ... and area lights
-template <int INLINE_LIGHTS = 0, bool AREA = false>
+template <int INLINE_LIGHTS = 0, bool AREA = false, bool LAMBERT = false>
 __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, const Basis& bl, f3 pos, float us, float u1, float u2, float ul) {
     f3 wl = mk3(0, 0, 0);
     float acc = 0.0f;
@@ -268,7 +272,7 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
         if (lo < S.n_lights) { from_light = true; wl = light_sample_dir(S.lights_g[lo], pos, u1, u2); }
         acc = __ldg(&S.light_cdf[S.n_lights - 1]);
     }
-    f3 ws = sdf_sample(sdf, bn, bl, u1, u2, ul);
+    f3 ws = sdf_sample<LAMBERT>(sdf, bn, bl, u1, u2, ul);
     if (from_light) return wl;
     acc += S.sdf_weight;
     if (us < acc) return ws;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                 if (go) {
                     double dd = (double)IPT_INF;
                     a_t = IPT_INF; a_prim = IPT_NO_HIT;
-                    analytic_closest<false, SPEC == SPEC_BOX_SCENE>(S, o, d, dd, a_t, a_prim);
+                    analytic_closest<false, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, dd, a_t, a_prim);
                     best_t = a_t; best_orig = IPT_NO_HIT; best_pos = IPT_NO_HIT;
                     have = true;
                     if (S.n_tris == 1) {
