@@ -66,9 +66,11 @@ class ProgressiveSession:
         return self.plane.display(self.glare_cutoff)[0]
 
     def set_glare_cutoff(self, wheel: int):
-        """Mouse wheel (gui.cpp:141-145): cutoff *= sqrt(2)^wheel."""
+        """Mouse wheel (gui.cpp:141-145): `glare_cutoff *= pow(sqrt(2.0f), wheel)` — float sqrt, pow and product in double
+        (std::pow(float, int) promotes), rounded back to the float member."""
         import numpy as np
-        self.glare_cutoff = float(np.float32(self.glare_cutoff) * np.float32(np.power(np.sqrt(np.float32(2.0)), wheel)))
+        factor = np.power(np.float64(np.sqrt(np.float32(2.0))), int(wheel))
+        self.glare_cutoff = float(np.float32(np.float64(np.float32(self.glare_cutoff)) * factor))
 
     def save(self, path="result.png"):
         """Gui::save (gui.cpp:192-194)."""
