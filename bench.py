@@ -40,7 +40,7 @@ WORKLOADS = {
                text="Cornell-box-style scene 'cornell' (5 box planes, Lambert sphere, glossy sphere, ceiling area light)"),
     "c3": dict(config="configs[2]", scene="mesh:1000000", width=1920, height=1080, depth_max=8, schedule=[1] * 8, spp_total=256, passes_per_step=4,
                text="procedural 1M-triangle random mesh inside the open box, max depth 8"),
-    "c4": dict(config="configs[3]", scene="mesh:10000000", width=3840, height=2160, depth_max=8, schedule=[1] * 8, spp_total=4096, passes_per_step=1,
+    "c4": dict(config="configs[3]", scene="mesh:10000000", width=3840, height=2160, depth_max=8, schedule=[1] * 8, spp_total=4096, passes_per_step=4,
                text="10M-triangle synthetic mesh, sample-sharded across the GPUs"),
     "c5": dict(config="configs[4]", scene="lightgrid:100x100", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], spp_total=16, passes_per_step=1,
                tile=(768, 768, 512, 512), text="many-light CollectionLighting scene (10k emitters), 512x512 crop of the 2048x2048 frame per step"),
@@ -177,7 +177,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "path-tracing throughput", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_text(), "parallelism": f"{pool.cores} host processes"},
+        "config": cpu_config(pool),
         "mrays_per_s": rays / dt / 1e6, "rays_per_path": rays / max(paths, 1),
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": pool.cores, "kind": pool.kind, "sample": pool.sample_text(args.steps),
                          "cpu": cpu_model()},
@@ -186,6 +186,16 @@ def run_reference_arm(args):
     }
     pool.close()
     print(json.dumps(line), flush=True)
+
+
+def cpu_config(pool):
+    """What the CPU legs really render: the workload's view and estimator on a small sample frame (a rate in paths/s does
+    not depend on the frame size or the pass count; a 1024x1024x1024-spp job would take the 16 host cores about an hour)."""
+    w = WORKLOAD
+    return {"workload": workload_text() + f" -- CPU leg: the same scene, view and estimator on a {CPU_SAMPLE['width']}x{CPU_SAMPLE['height']} sample frame",
+            "sample_width": CPU_SAMPLE["width"], "sample_height": CPU_SAMPLE["height"], "sample_passes_per_step_per_core": 1,
+            "job_width": w["width"], "job_height": w["height"], "same_config": False,
+            "parallelism": f"{pool.cores} host processes"}
 
 
 def workload_text():
@@ -237,163 +247,303 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Dist:
+    """torch.distributed plumbing of one process per GPU (N = 1: everything is a no-op)."""
+
+    def __init__(self):
+        import torch
+
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.comm = None
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            from ipt_b200 import nccl_comm
+
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local}"))
+            self.dist = dist
+            # the ncclComm_t handed to the product's collective (ipt_plane_allreduce); torch only ships the unique id
+            self.comm = nccl_comm.NcclComm(dist, self.rank, self.world)
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="sum"):
+        """Scalars over all ranks (bookkeeping, outside the timed regions)."""
+        if self.dist is None:
+            return [float(v) for v in values]
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op={"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}[op])
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+AGG_KEYS = ("paths", "rays", "kernel_launches", "ms_total", "ms_extend", "ms_shade", "ms_generate", "ms_accumulate", "n_extend", "n_shade",
+            "surface_hits", "light_hits", "queue_bytes", "rays_resolved_in_shade", "bvh_nodes_visited", "triangles_tested", "lights_tested",
+            "light_bvh_nodes_visited")
+
+
+def measure(D, w, steps, warmup, pps, args, ranks_active=None, e2e_steps=0):
+    """Times `steps` steps of workload `w` on every active rank (default: all) and returns the measurements of the line.
+    A step = `pps` passes of the frame (or of its tile). Device-resident part: scene and accumulators stay in HBM, the
+    accumulators of all ranks are merged once at the end by the product's collective. End-to-end part: every step goes
+    through the C ABI with the camera coming from the host and the merged accumulators going back to pinned host memory."""
     import torch
-    import torch.distributed as dist
 
-    from ipt_b200 import build, capi
+    from ipt_b200 import capi
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    build.build()
     lib = capi.load()
-    w = WORKLOAD
+    active = ranks_active is None or D.rank in ranks_active
+    n_active = D.world if ranks_active is None else len(ranks_active)
     W, H = w["width"], w["height"]
-    pps = args.passes_per_step
-    sd = capi.SceneDescription(w["scene"])
-    sc = capi.Scene(sd, local)
-    # accumulators are torch tensors so that NCCL can reduce them in place; the library accumulates into them
-    acc_sum = torch.zeros(H * W, dtype=torch.float32, device="cuda")
-    acc_sq = torch.zeros(H * W, dtype=torch.float32, device="cuda")
-    acc_cnt = torch.zeros(H * W, dtype=torch.int32, device="cuda")
-    plane = capi.Plane(sc, W, H, wrap=(acc_sum.data_ptr(), acc_sq.data_ptr(), acc_cnt.data_ptr()))
-    total_steps = args.warmup + args.steps
-    first_pass = rank * total_steps * pps  # disjoint pass ranges per rank
-
     tile = w.get("tile")
     paths_per_pass = (tile[2] * tile[3]) if tile else W * H
+    out = dict(n_active=n_active, paths_per_pass=paths_per_pass)
+    sd = sc = plane = None
+    if active:
+        t0 = time.perf_counter()
+        sd = capi.SceneDescription(w["scene"])
+        sc = capi.Scene(sd, D.local)
+        plane = capi.Plane(sc, W, H)  # library-owned accumulators: one packed block sum | sumsq | count
+        out["scene_setup_s"] = time.perf_counter() - t0
+    first_pass = D.rank * (warmup + steps + e2e_steps + 1) * pps  # disjoint pass ranges per rank
 
     def params(step, flags=capi.FLAG_TIME_KERNELS):
         kw = dict(tile_x0=tile[0], tile_y0=tile[1], tile_w=tile[2], tile_h=tile[3]) if tile else {}
         return capi.default_params(width=W, height=H, depth_max=w["depth_max"], schedule=w["schedule"], seed=args.seed,
                                    pass_begin=first_pass + step * pps, pass_count=pps, flags=flags, batch_paths=args.batch_paths, **kw)
 
-    def sync():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- device-resident throughput: the scene is in HBM, accumulators stay in HBM ----
-    for s in range(args.warmup):
-        plane.render(params(s))
-    acc_sum.zero_(); acc_sq.zero_(); acc_cnt.zero_()
-    sampler = ClockSampler(local)
+    use_comm = D.comm is not None and ranks_active is None
+    agg = {k: 0.0 for k in AGG_KEYS}
+    coll_ms = 0.0
+    if active:
+        for s_ in range(warmup):
+            plane.render(params(s_))
+        if use_comm:
+            plane.allreduce(D.comm.comm)  # full-size warm-up of the collective: ring / NVLS set-up is not part of the job
+        plane.clear()
+    sampler = ClockSampler(D.local)
     sampler.start()
-    agg = dict(paths=0, rays=0, launches=0, ms_dev=0.0, ms_ext=0.0, ms_shade=0.0, ms_gen=0.0, ms_acc=0.0, n_ext=0, n_shade=0, queued=0,
-               surface=0, light=0, queue_bytes=0, nodes=0, tris=0, fused=0)
-    sync()
+    D.sync()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        st = plane.render(params(args.warmup + s))
-        agg["paths"] += st.paths; agg["rays"] += st.rays; agg["launches"] += st.kernel_launches; agg["ms_dev"] += st.ms_total
-        agg["ms_ext"] += st.ms_extend; agg["ms_shade"] += st.ms_shade; agg["ms_gen"] += st.ms_generate; agg["ms_acc"] += st.ms_accumulate
-        agg["n_ext"] += st.n_extend; agg["n_shade"] += st.n_shade; agg["surface"] += st.surface_hits; agg["light"] += st.light_hits
-        agg["queue_bytes"] += st.queue_bytes; agg["fused"] += st.rays_resolved_in_shade; agg["nodes"] += st.bvh_nodes_visited; agg["tris"] += st.triangles_tested
-    if world > 1:  # the only collective of the path: reduce the accumulators over NVLink
-        dist.all_reduce(acc_sum); dist.all_reduce(acc_sq); dist.all_reduce(acc_cnt)
-    sync()
+    if active:
+        for s_ in range(steps):
+            st = plane.render(params(warmup + s_))
+            for k in AGG_KEYS:
+                agg[k] += getattr(st, k)
+        if use_comm:  # the only collective of the path: merge the accumulators over NVLink (ipt_plane_allreduce)
+            coll_ms = plane.allreduce(D.comm.comm)
+    D.sync()
     elapsed = time.perf_counter() - t0
-    clocks = sampler.result()
-    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([agg["paths"], agg["rays"], agg["launches"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot)
-    elapsed = float(t.item())
-    paths_all, rays_all, launches_all = (float(x) for x in tot.tolist())
-    image_mean = float(acc_sum.sum().item() / max(int(acc_cnt.sum().item()), 1))
+    out["clocks"] = sampler.result()
+    out["elapsed"] = D.reduce([elapsed], "max")[0]
+    tot = D.reduce([agg["paths"], agg["rays"], agg["kernel_launches"]])
+    out["paths_all"], out["rays_all"], out["launches_all"] = tot
+    dev_ms = agg["ms_total"] / max(steps, 1) if active else 0.0
+    out["device_ms_per_step_max"] = D.reduce([dev_ms], "max")[0]
+    out["device_ms_per_step_min"] = D.reduce([dev_ms if active else 1e30], "min")[0]
+    out["collective_ms"] = D.reduce([coll_ms], "max")[0]
+    out["agg"] = agg
+    if active and D.rank == 0:
+        s_, q_, c_ = plane.download()
+        out["image_mean"] = float(s_.sum(dtype=np.float64) / max(int(c_.sum(dtype=np.uint64)), 1))
 
-    # ---- end to end through the C ABI with HOST buffers: per step camera in, sum/sumsq/count out ----
-    cam = sd.desc.camera
+    # ---- end to end through the C ABI with HOST buffers --------------------------------------------------------------
+    if e2e_steps:
+        cam = sd.desc.camera if active else None
+        host_out = None
+        if active and D.rank == 0 or (active and not use_comm):
+            host_out = (torch.empty(H * W, dtype=torch.float32).pin_memory().numpy(), torch.empty(H * W, dtype=torch.float32).pin_memory().numpy(),
+                        torch.empty(H * W, dtype=torch.int32).pin_memory().numpy().view(np.uint32))
+
+        def e2e_step(step):
+            capi.check(lib.ipt_scene_set_camera(sc.handle, C.byref(cam)))  # this step's input: the camera, from the host
+            if not use_comm:
+                hs, hq, hc, st = sc.render_host(params(step, flags=0), out=host_out)  # clear + render + download
+                return st.paths, float(hs.reshape(-1)[0])
+            plane.clear()
+            st = plane.render(params(step, flags=0))
+            plane.allreduce(D.comm.comm)  # merged on the device over NVLink ...
+            v = 0.0
+            if D.rank == 0:  # ... and read where the user reads the image
+                plane.download_into(*host_out)
+                v = float(host_out[0][0])
+            return st.paths, v
+
+        if active:
+            e2e_step(warmup + steps)  # warm the staging path
+        D.sync()
+        t0 = time.perf_counter()
+        e2e_paths = 0
+        if active:
+            for s_ in range(e2e_steps):
+                p_, _ = e2e_step(warmup + steps + 1 + s_)
+                e2e_paths += p_
+        D.sync()
+        e2e_elapsed = D.reduce([time.perf_counter() - t0], "max")[0]
+        out["e2e_value"] = D.reduce([e2e_paths])[0] / e2e_elapsed / 1e6
+        out["e2e_steps"] = e2e_steps
+        out["h2d_bytes_per_step"] = C.sizeof(capi.Camera) + C.sizeof(capi.RenderParams)
+        out["d2h_bytes_per_step"] = 12 * W * H
+    if active:
+        plane.close()
+        sc.close()
+    return out
+
+
+def roofline_block(m, w, args):
+    """The dominant kernel against the HBM roofline of SURVEY.md 8d, and what really binds it.
+
+    `achieved` = ALGORITHMIC bytes / CUDA-event time of the dominant kernel: the wavefront model of SURVEY 8d (every ray a
+    36 B record written once and read once, every queued hit a 32 B record written once and read once, plus 64 B per BVH
+    node visit and per triangle / light record fetched). The fused shade kernels never queue the rays they trace, so the
+    bytes they really move (`implemented_bytes_per_launch`, and ncu's `traffic`) are far below the model and the kernel is
+    bound by instruction issue, not by HBM: `binding` says so and `issue_frac` is ncu's issue-slot utilisation."""
+    agg = m["agg"]
+    peak, peak_src = measured_peak()
+    children = agg["rays"] - agg["paths"]
+    queued = (agg["queue_bytes"] - 72 * agg["rays"] - 8 * agg["paths"]) // 64
+    fused = agg["rays_resolved_in_shade"]
+    nodes, tris = agg["bvh_nodes_visited"], agg["triangles_tested"]
+    lnodes = agg["light_bvh_nodes_visited"]
+    lrecs = agg["lights_tested"] if lnodes else 0  # inline / linear light lists live in the constant bank or L1
+    scene_bytes = 64 * (nodes + tris) + 64 * lnodes + 128 * lrecs
+    hits_by_shade = max(queued - agg["paths"], 0) if fused == children and fused else 0  # all but the camera rays' hits
+    bytes_ext = 36 * (agg["rays"] - fused) + 32 * (queued - hits_by_shade) + 8 * agg["light_hits"] * (0 if fused else 1) + 64 * (nodes + tris)
+    bytes_shade = 32 * queued + 36 * children + 36 * fused + 32 * hits_by_shade + 8 * agg["light_hits"] * (1 if fused else 0)
+    bytes_shade_impl = 32 * queued + 36 * (children - fused) + 32 * hits_by_shade + 8 * agg["light_hits"] * (1 if fused else 0)
+    if fused:
+        bytes_shade += 64 * lnodes + 128 * lrecs
+        bytes_shade_impl += 64 * lnodes + 128 * lrecs
+    else:
+        bytes_ext += 64 * lnodes + 128 * lrecs
+    dom = "shade" if agg["ms_shade"] >= agg["ms_extend"] else "extend"
+    dom_ms = agg["ms_shade"] if dom == "shade" else agg["ms_extend"]
+    dom_n = agg["n_shade"] if dom == "shade" else agg["n_extend"]
+    dom_bytes = bytes_shade if dom == "shade" else bytes_ext
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    avg_ms = dom_ms / max(dom_n, 1)
+    # SURVEY 8d's own per-ray figures (96 B per ray, 32 B per node, 36 B per triangle, 24 B per path), whole pipeline
+    survey_bytes = 96 * agg["rays"] + 32 * nodes + 36 * tris + 48 * (agg["lights_tested"] if lnodes else 0) + 32 * lnodes + 24 * agg["paths"]
+    whole_bytes = agg["queue_bytes"] + scene_bytes
+    block = {"bound": "hbm", "kernel": ("k_extend_mesh" if dom == "extend" and w["scene"].startswith("mesh") else f"k_{dom}"),
+             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+             "launches": int(dom_n), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": dom_bytes / max(dom_n, 1),
+             "implemented_bytes_per_launch": (bytes_shade_impl if dom == "shade" else bytes_ext) / max(dom_n, 1),
+             "model": "SURVEY 8d wavefront queue model: 36 B ray record written + read per ray, 32 B hit record written + read per queued hit, "
+                      "64 B per BVH node visit / triangle record, 128 B per light record of a light LBVH",
+             "whole_pipeline": {"bytes": whole_bytes, "achieved_gbs": whole_bytes / (agg["ms_total"] * 1e-3) / 1e9,
+                                "frac": whole_bytes / (agg["ms_total"] * 1e-3) / 1e9 / peak},
+             "survey_8d": {"formula": "96 R + 32 V + 36 T + 48 L + 32 V_L + 24 P", "bytes": survey_bytes,
+                           "achieved_gbs": survey_bytes / (agg["ms_total"] * 1e-3) / 1e9, "frac": survey_bytes / (agg["ms_total"] * 1e-3) / 1e9 / peak},
+             "kernel_ms": {"generate": agg["ms_generate"], "extend": agg["ms_extend"], "shade": agg["ms_shade"], "accumulate": agg["ms_accumulate"]},
+             "per_ray": {"bvh_nodes": nodes / max(agg["rays"], 1), "triangles": tris / max(agg["rays"], 1),
+                         "light_bvh_nodes": lnodes / max(agg["rays"], 1), "lights": agg["lights_tested"] / max(agg["rays"], 1)}}
+    # profile-time evidence (ncu cannot run inside the timed region): DRAM bytes per launch and issue-slot utilisation
+    # of the dominant kernel from the committed capture, with the source hash it was taken on
+    prof = ROOT / "profiles" / "roofline_latest.json"
+    if prof.exists() and not args.batch_paths:
+        try:
+            pj = json.loads(prof.read_text())
+            rec = pj.get("workloads", {}).get(args.workload, {}).get(dom)
+            if rec:
+                block["traffic"] = rec.get("dram_bytes_per_launch")
+                block["traffic_source"] = f"profile-time: ncu capture {pj.get('source', '')}; kernel sources then {pj.get('source_sha16')}, now {source_sha16()}"
+                if block["traffic"]:
+                    block["dram_gbs"] = block["traffic"] / (avg_ms * 1e-3) / 1e9
+                    block["dram_frac"] = block["dram_gbs"] / peak
+                if rec.get("issue_active_pct") is not None:
+                    block["issue_frac"] = rec["issue_active_pct"] / 100.0
+                    block["active_lanes_per_instruction"] = rec.get("lanes_per_inst")
+        except Exception:
+            pass
+    traffic = block["traffic"]
+    block["binding"] = ("instruction issue (model bytes are credited, not moved: the fused kernels keep the rays on chip)"
+                        if traffic is not None and traffic < 0.5 * block["algorithmic_bytes_per_launch"] else "hbm / L2 latency")
+    return block
+
+
+def source_sha16():
+    import hashlib
+
+    h = hashlib.sha256()
+    for p in sorted((ROOT / "ipt_b200" / "csrc").glob("*.cu*")):
+        h.update(p.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def run_ours(args):
+    from ipt_b200 import build, capi
+
+    D = Dist()
+    build.build()
+    capi.load()
+    w = WORKLOAD
+    pps = args.passes_per_step
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    # the caller's result buffers: pinned host memory, reused every step
-    host_out = (torch.empty(H * W, dtype=torch.float32).pin_memory().numpy(), torch.empty(H * W, dtype=torch.float32).pin_memory().numpy(),
-                torch.empty(H * W, dtype=torch.int32).pin_memory().numpy().view(np.uint32))
-    sc.render_host(params(args.warmup, flags=0), out=host_out)  # warm the host plane / staging path
-    sync()
-    t0 = time.perf_counter()
-    e2e_paths = 0
-    for s in range(e2e_steps):
-        capi.check(lib.ipt_scene_set_camera(sc.handle, C.byref(cam)))
-        hs, hq, hc, st = sc.render_host(params(args.warmup + s, flags=0), out=host_out)
-        e2e_paths += st.paths
-        if world > 1:  # N GPUs: the per-rank results are merged where the user reads them
-            part = torch.from_numpy(hs).cuda()
-            dist.all_reduce(part)
-            hs = part.cpu().numpy()
-        _ = float(hs[0, 0])
-    sync()
-    e2e_elapsed = time.perf_counter() - t0
-    t = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
-    ep = torch.tensor([e2e_paths], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ep)
-    e2e_value = float(ep.item()) / float(t.item()) / 1e6
-
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        # dominant kernel and its algorithmic bytes: the wavefront MODEL of SURVEY.md §8d — every ray
-        # is a 36 B record written once and read once, every queued hit a 32 B record written once and read once.
-        # The fused shade kernels trace the children they spawn, so those rays are never queued: a fused launch is
-        # credited with the model bytes of the two kernels it replaces (36 B write + 36 B read per such ray, the hit
-        # record it appends, 8 B per light hit), and `implemented_bytes_per_launch` says what the implementation itself
-        # has to move (hit records in and out, path values).
-        children = agg["rays"] - agg["paths"]
-        queued = (agg["queue_bytes"] - 72 * agg["rays"] - 8 * agg["paths"]) // 64
-        fused = agg["fused"]
-        hits_by_shade = max(queued - agg["paths"], 0) if fused == children and fused else 0  # all but the camera rays' hits
-        bytes_ext = 36 * (agg["rays"] - fused) + 32 * (queued - hits_by_shade) + 8 * agg["light"] * (0 if fused else 1) + 64 * (agg["nodes"] + agg["tris"])
-        bytes_shade = 32 * queued + 36 * children + 36 * fused + 32 * hits_by_shade + 8 * agg["light"] * (1 if fused else 0)
-        bytes_shade_impl = 32 * queued + 36 * (children - fused) + 32 * hits_by_shade + 8 * agg["light"] * (1 if fused else 0)
-        dom = "shade" if agg["ms_shade"] >= agg["ms_ext"] else "extend"
-        dom_ms = agg["ms_shade"] if dom == "shade" else agg["ms_ext"]
-        dom_n = agg["n_shade"] if dom == "shade" else agg["n_ext"]
-        dom_bytes = bytes_shade if dom == "shade" else bytes_ext
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        traffic = None
-        prof = ROOT / "profiles" / "roofline_latest.json"
-        if prof.exists() and args.workload == "c2" and not args.batch_paths:  # the ncu capture is of this workload at the default batch
-            try:
-                traffic = json.loads(prof.read_text()).get(dom, {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+    m = measure(D, w, args.steps, args.warmup, pps, args, e2e_steps=e2e_steps)
+    elapsed = m["elapsed"]
+    line = None
+    if D.rank == 0:
         line = {
-            "metric": "path-tracing throughput", "value": paths_all / elapsed / 1e6, "unit": "Mpaths/s", "n_gpus": world,
+            "metric": "path-tracing throughput", "value": m["paths_all"] / elapsed / 1e6, "unit": "Mpaths/s", "n_gpus": D.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_text(), "passes_per_step": pps, "paths_per_step_per_gpu": paths_per_pass * pps,
-                       "parallelism": f"pass-sharded x{world}" if world > 1 else "single GPU",
+            "config": {"workload": workload_text(), "passes_per_step": pps, "paths_per_step_per_gpu": m["paths_per_pass"] * pps,
+                       "parallelism": f"pass-sharded x{D.world}, accumulators merged once by ipt_plane_allreduce (NCCL)" if D.world > 1 else "single GPU",
                        "l2": "per-step ray/hit queue working set (>1 GB) exceeds the 126 MB L2; no flush needed",
-                       "batch_paths": args.batch_paths or "library default (2^28 / widest queued tree level = 2^21 paths)"},
-            "mrays_per_s": rays_all / elapsed / 1e6, "rays_per_path": rays_all / max(paths_all, 1), "image_mean": image_mean,
-            "device_ms_per_step": agg["ms_dev"] / args.steps,
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(capi.Camera) + C.sizeof(capi.RenderParams),
-                    "d2h_bytes_per_step": 12 * W * H, "steps": e2e_steps,
-                    "call": "ipt_scene_set_camera + ipt_render_host (host sum/sumsq/count buffers)"},
-            "gpu_launches": int(launches_all),
-            "roofline": {"bound": "hbm", "kernel": ("k_extend_mesh" if dom == "extend" and w["scene"].startswith("mesh") else f"k_{dom}"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "launches": dom_n, "avg_launch_ms": dom_ms / max(dom_n, 1),
-                         "algorithmic_bytes_per_launch": dom_bytes / max(dom_n, 1),
-                         "implemented_bytes_per_launch": (bytes_shade_impl if dom == "shade" else bytes_ext) / max(dom_n, 1),
-                         "model": "SURVEY 8d wavefront queue model: 36 B ray record written + read per ray, 32 B hit record written + read per queued hit",
-                         "whole_pipeline": {"bytes": agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"]),
-                                            "achieved_gbs": (agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"])) / (agg["ms_dev"] * 1e-3) / 1e9,
-                                            "frac": (agg["queue_bytes"] + 64 * (agg["nodes"] + agg["tris"])) / (agg["ms_dev"] * 1e-3) / 1e9 / peak},
-                         "kernel_ms": {"generate": agg["ms_gen"], "extend": agg["ms_ext"], "shade": agg["ms_shade"], "accumulate": agg["ms_acc"]}},
+                       "batch_paths": args.batch_paths or "library default"},
+            "mrays_per_s": m["rays_all"] / elapsed / 1e6, "rays_per_path": m["rays_all"] / max(m["paths_all"], 1), "image_mean": m.get("image_mean"),
+            "device_ms_per_step": m["agg"]["ms_total"] / args.steps,
+            "device_ms_per_step_ranks": {"min": m["device_ms_per_step_min"], "max": m["device_ms_per_step_max"]},
+            "collective_ms": m["collective_ms"],
+            "host_overhead_ms_per_step": elapsed / args.steps * 1e3 - m["device_ms_per_step_max"] - m["collective_ms"] / args.steps,
+            "clocks": m["clocks"],
+            "e2e": {"value": m["e2e_value"], "unit": "Mpaths/s", "h2d_bytes_per_step": m["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": m["d2h_bytes_per_step"], "steps": m["e2e_steps"],
+                    "call": ("ipt_scene_set_camera + ipt_render_host (host sum/sumsq/count buffers)" if D.world == 1 else
+                             "per step: ipt_scene_set_camera + ipt_plane_clear + ipt_render + ipt_plane_allreduce on every rank, ipt_plane_download to pinned host memory on rank 0")},
+            "gpu_launches": int(m["launches_all"]),
+            "roofline": roofline_block(m, w, args),
         }
-        if world == 1 and not args.no_cpu_baseline and w["scene"] not in ("box", "cornell"):
+    # BASELINE configs[3] (the multi-GPU config) rides along on N > 1: same invocation, its own sub-record
+    if (D.world > 1 or args.with_c4) and args.workload == "c2" and not args.no_c4:
+        c4 = dict(WORKLOADS["c4"])
+        k4, w4, p4 = args.c4_steps, 2, c4["passes_per_step"]
+        one = measure(D, c4, k4, w4, p4, args, ranks_active=[0]) if D.world > 1 else None  # rank 0 alone: the 1-GPU denominator, same box
+        alln = measure(D, c4, k4, w4, p4, args, e2e_steps=min(k4, 4))
+        if D.rank == 0:
+            rec = {"workload": f"BASELINE {c4['config']}: {c4['text']}, {c4['width']}x{c4['height']}, depth {c4['depth_max']}, split schedule 1x8",
+                   "n_gpus": D.world, "steps": k4, "warmup": w4, "passes_per_step": p4,
+                   "value": alln["paths_all"] / alln["elapsed"] / 1e6, "unit": "Mpaths/s", "mrays_per_s": alln["rays_all"] / alln["elapsed"] / 1e6,
+                   "ms_per_step": alln["elapsed"] / k4 * 1e3, "device_ms_per_step_ranks": {"min": alln["device_ms_per_step_min"], "max": alln["device_ms_per_step_max"]},
+                   "collective_ms": alln["collective_ms"], "e2e": {"value": alln["e2e_value"], "unit": "Mpaths/s", "d2h_bytes_per_step": alln["d2h_bytes_per_step"]},
+                   "scene_setup_s": alln.get("scene_setup_s"), "image_mean": alln.get("image_mean"), "roofline": roofline_block(alln, c4, args)}
+            if one is not None:
+                v1 = one["paths_all"] / one["elapsed"] / 1e6
+                rec["one_gpu_same_box"] = {"value": v1, "unit": "Mpaths/s", "ms_per_step": one["elapsed"] / k4 * 1e3}
+                rec["speedup_vs_one_gpu"] = rec["value"] / v1
+            line["c4"] = rec
+    if D.rank == 0:
+        if D.world == 1 and not args.no_cpu_baseline and w["scene"] not in ("box", "cornell"):
             line["cpu_baseline"] = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "port",
                                     "sample": "not run: the reference has no mesh / 10k-light scene; see the c1/c2 workloads"}
-        elif world == 1 and not args.no_cpu_baseline:
+        elif D.world == 1 and not args.no_cpu_baseline:
             pool = CpuPool()
             paths = rays = 0
             t0 = time.perf_counter()
@@ -403,13 +553,11 @@ def run_ours(args):
                 paths += p; rays += r; reps += 1
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": paths / dt / 1e6, "unit": "Mpaths/s", "cores": pool.cores, "kind": pool.kind,
-                                    "sample": pool.sample_text(reps), "mrays_per_s": rays / dt / 1e6, "cpu": cpu_model()}
+                                    "sample": pool.sample_text(reps), "mrays_per_s": rays / dt / 1e6, "cpu": cpu_model(),
+                                    "config": cpu_config(pool)}
             pool.close()
         print(json.dumps(line), flush=True)
-    plane.close()
-    sc.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 def main():
@@ -425,6 +573,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-c4", action="store_true", help="add the BASELINE configs[3] sub-record on one GPU too (always on for N > 1)")
+    ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--c4-steps", type=int, default=6)
     args = ap.parse_args()
     WORKLOAD.clear()
     WORKLOAD.update(WORKLOADS[args.workload])

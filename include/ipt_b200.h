@@ -25,8 +25,18 @@
 extern "C" {
 #endif
 
-#define IPT_B200_ABI_VERSION 2
+#define IPT_B200_ABI_VERSION 3
 #define IPT_MAX_DEPTH 16
+/* The random numbers of a render: Philox4x32 (Salmon et al. 2011) with IPT_PHILOX_ROUNDS rounds, key = seed, counter =
+ * (loop pixel, pass, node index within its tree level, depth); the four 32-bit outputs become uniforms in [0,1) with
+ * IPT_U01_BITS bits: (x >> (32 - bits)) * 2^-bits. Shared by the device code and the CPU oracle so that both draw the
+ * same numbers. */
+#ifndef IPT_PHILOX_ROUNDS
+#define IPT_PHILOX_ROUNDS 10
+#endif
+#ifndef IPT_U01_BITS
+#define IPT_U01_BITS 23
+#endif
 #define IPT_NO_HIT 0xFFFFFFFFu
 
 enum ipt_status {
@@ -123,7 +133,8 @@ enum ipt_plane_mode {
 enum ipt_render_flags {
     IPT_FLAG_TIME_KERNELS = 1u, /* bracket every kernel with CUDA events on the render stream -> ipt_render_stats::ms_* */
     IPT_FLAG_KEEP_ZERO_WEIGHT = 2u, /* trace children whose weight is exactly 0 (the reference does, main.cpp:177) */
-    IPT_FLAG_DEBUG_PRINT = 4u,      /* device printf of every ray / sample (single-path debugging) */
+    IPT_FLAG_DEBUG_PRINT = 4u,      /* device printf of every ray / sample (single-path debugging); only in a library built with
+                                     * -DIPT_DEBUG_PRINT, else IPT_ERR_UNSUPPORTED: the production kernels carry no printf */
     /* At the last traced depth a ray only matters if it reaches a light, so by default the geometry is intersected
      * only for rays that hit a light ("shadow ray"); with this flag every last-level ray is resolved into
      * surface hit / miss as well, which only affects ipt_render_stats::surface_hits / misses. */
@@ -158,7 +169,9 @@ typedef struct ipt_render_stats {
     uint64_t failed_samples;           /* zero-vector samples (lighting.cpp:55-56); still in the 1/n divisor */
     uint64_t zero_weight_pruned;       /* children with weight exactly 0 that were not traced */
     uint64_t nonfinite_dropped;        /* non-finite weights/values dropped (main.cpp:175,181,215) */
-    uint64_t bvh_nodes_visited, triangles_tested, lights_tested;
+    uint64_t bvh_nodes_visited, triangles_tested; /* mesh LBVH (device counters) */
+    uint64_t lights_tested;            /* Light::traceRay evaluations of traced rays (device counter, any light container) */
+    uint64_t light_bvh_nodes_visited;  /* node visits of the light LBVH (many-light scenes; device counter) */
     uint32_t batches;
     uint32_t kernel_launches;          /* kernels of this library launched by the call */
     float ms_total;                    /* device time of the whole call (CUDA events) */
@@ -230,6 +243,11 @@ int ipt_light_ddf_value(ipt_scene* scene, const float pos[3], const float* dirs,
 /* Lighting::distributionInPoint(pos)->sample(): n directions (zero vector = failed sample), Philox stream (seed, index). */
 int ipt_light_ddf_sample(ipt_scene* scene, const float pos[3], uint64_t seed, size_t n, float* dirs);
 
+/* randf (include/randf.h:6-11) on the device: the render's random stream. For each of n counters (4 x uint32: loop pixel,
+ * pass, node, depth) the Philox4x32-IPT_PHILOX_ROUNDS block keyed by `seed` (4 x uint32) and its four uniforms
+ * (4 x float, see IPT_U01_BITS). HOST arrays; either output may be NULL. */
+int ipt_philox_batch(int device, const uint32_t* counters, size_t n, uint64_t seed, uint32_t* blocks, float* uniforms);
+
 /* LBVH over the triangle mesh, as built on the device: n_triangles-1 internal nodes of 64 bytes (root = 0), each
  * holding BOTH children's boxes; the sorted primitive order; the sorted 63-bit Morton keys. */
 typedef struct ipt_bvh_node {
@@ -259,8 +277,10 @@ int ipt_plane_device_ptrs(ipt_plane* plane, float** d_sum, float** d_sumsq, uint
 /* The path's ONLY collective: element-wise sum of sum / sumsq / count over all ranks of an NCCL communicator (one
  * process or thread per GPU, each rendering its own pass range; replaces the mutex-guarded running mean that merges the
  * reference's four threads, src/gui.cpp:165-182). `nccl_comm` is an ncclComm_t owned by the host application. The
- * library links against no NCCL: it resolves ncclAllReduce from the NCCL already loaded in the process (libnccl.so.2). */
-int ipt_plane_allreduce(ipt_plane* plane, void* nccl_comm);
+ * library links against no NCCL: it resolves ncclAllReduce from the NCCL already loaded in the process (libnccl.so.2).
+ * One grouped launch (ncclGroupStart/End): the two float arrays as one message when they are contiguous (they are in a
+ * plane made by ipt_plane_create: one packed block sum | sumsq | count), then the counters. */
+int ipt_plane_allreduce(ipt_plane* plane, void* nccl_comm, float* ms /* device time of the collective, may be NULL */);
 /* GridRenderPlane state after the same samples: pixels = sum/count, pixel_counters, max_value (GridRenderPlane.h:9-12). */
 int ipt_plane_resolve(ipt_plane* plane, float* pixels, uint64_t* pixel_counters, float* max_value);
 

@@ -64,7 +64,7 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("rays_at_depth", C.c_uint64 * IPT_MAX_DEPTH),
                 ("surface_hits", C.c_uint64), ("light_hits", C.c_uint64), ("misses", C.c_uint64),
                 ("failed_samples", C.c_uint64), ("zero_weight_pruned", C.c_uint64), ("nonfinite_dropped", C.c_uint64),
-                ("bvh_nodes_visited", C.c_uint64), ("triangles_tested", C.c_uint64), ("lights_tested", C.c_uint64),
+                ("bvh_nodes_visited", C.c_uint64), ("triangles_tested", C.c_uint64), ("lights_tested", C.c_uint64), ("light_bvh_nodes_visited", C.c_uint64),
                 ("batches", C.c_uint32), ("kernel_launches", C.c_uint32), ("ms_total", C.c_float),
                 ("ms_generate", C.c_float), ("ms_extend", C.c_float), ("ms_shade", C.c_float), ("ms_accumulate", C.c_float),
                 ("n_extend", C.c_uint32), ("n_shade", C.c_uint32), ("queue_bytes", C.c_uint64),
@@ -107,6 +107,7 @@ SIGNATURES = {
     "ipt_mix_sample": (C.c_int, [_vp, f32p, f32p, C.c_uint64, C.c_size_t, f32p, f32p, f32p]),
     "ipt_light_ddf_value": (C.c_int, [_vp, f32p, f32p, C.c_size_t, f32p]),
     "ipt_light_ddf_sample": (C.c_int, [_vp, f32p, C.c_uint64, C.c_size_t, f32p]),
+    "ipt_philox_batch": (C.c_int, [C.c_int, u32p, C.c_size_t, C.c_uint64, u32p, f32p]),
     "ipt_bvh_export": (C.c_int, [_vp, C.POINTER(BvhNode), u32p, u64p, u64p]),
     "ipt_plane_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
     "ipt_plane_wrap": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
@@ -116,7 +117,7 @@ SIGNATURES = {
     "ipt_plane_download": (C.c_int, [_vp, f32p, f32p, u32p]),
     "ipt_plane_upload": (C.c_int, [_vp, f32p, f32p, u32p]),
     "ipt_plane_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
-    "ipt_plane_allreduce": (C.c_int, [_vp, _vp]),
+    "ipt_plane_allreduce": (C.c_int, [_vp, _vp, f32p]),
     "ipt_plane_resolve": (C.c_int, [_vp, f32p, u64p, f32p]),
     "ipt_image_glare": (C.c_int, [C.c_int, f32p, C.c_uint32, C.c_uint32, C.c_float, f32p, u32p]),
     "ipt_image_normalize": (C.c_int, [C.c_int, f32p, C.c_uint32, C.c_uint32, f32p]),
@@ -194,6 +195,15 @@ def image_save_bytes(image, device: int = 0):
 def write_png_gray8(path, image_u8):
     a = np.ascontiguousarray(image_u8, np.uint8); h, w = a.shape
     check(load().ipt_write_png_gray8(str(path).encode(), _ptr(a, u8p), w, h))
+
+
+def philox_batch(counters, seed: int = 0, device: int = 0):
+    """ipt_philox_batch: (blocks uint32[n,4], uniforms float32[n,4]) of the render's Philox stream for uint32[n,4] counters."""
+    c = np.ascontiguousarray(counters, dtype=np.uint32).reshape(-1, 4)
+    blocks = np.empty_like(c)
+    uni = np.empty(c.shape, np.float32)
+    check(load().ipt_philox_batch(device, _ptr(c, u32p), c.shape[0], seed, _ptr(blocks, u32p), _ptr(uni, f32p)))
+    return blocks, uni
 
 
 def camera_orbit(camera: Camera, key: int) -> Camera:
@@ -377,9 +387,15 @@ class Plane:
         c = np.ascontiguousarray(c, np.uint32).ravel()
         check(load().ipt_plane_upload(self.handle, _ptr(s, f32p), _ptr(q, f32p), _ptr(c, u32p)))
 
-    def allreduce(self, nccl_comm):
-        """ipt_plane_allreduce with an ncclComm_t (integer / c_void_p) of the calling process."""
-        check(load().ipt_plane_allreduce(self.handle, nccl_comm))
+    def allreduce(self, nccl_comm) -> float:
+        """ipt_plane_allreduce with an ncclComm_t (integer / c_void_p) of the calling process; returns its device time in ms."""
+        ms = C.c_float(0)
+        check(load().ipt_plane_allreduce(self.handle, nccl_comm, C.byref(ms)))
+        return ms.value
+
+    def download_into(self, s, q, c):
+        """ipt_plane_download into caller-owned (e.g. pinned) host arrays."""
+        check(load().ipt_plane_download(self.handle, _ptr(s, f32p), _ptr(q, f32p), _ptr(c, u32p)))
 
     def resolve(self):
         n = self.width * self.height

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -233,6 +234,14 @@ __global__ void k_light_ddf_sample(const __grid_constant__ DevScene S, f3 pos, u
     w[3 * i] = x.x; w[3 * i + 1] = x.y; w[3 * i + 2] = x.z;
 }
 
+__global__ void k_philox_batch(const uint4* __restrict__ c, size_t n, PhiloxKeys keys, uint4* blocks, float4* uniforms) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = philox4x32(c[i].x, c[i].y, c[i].z, c[i].w, keys);
+    if (blocks) blocks[i] = r;
+    if (uniforms) uniforms[i] = make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+
 __global__ void k_plane_add_rays(RenderCtx C, size_t n, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -348,6 +357,25 @@ static void set_camera(DevScene& dev, const ipt_camera& c) {
     std::memcpy(dev.cam.up, c.up, 12);
 }
 
+// Philox key schedule of a seed (ipt_device.cuh: philox4x32)
+static void philox_keys(uint64_t seed, PhiloxKeys& out) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < IPT_PHILOX_ROUNDS; ++r) {
+        out.k[2 * r] = k0; out.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// (mul, shift) of ipt_device.cuh's fastdiv: mul = floor(2^32 * (2^L - d) / d) + 1 with L = ceil(log2 d), shift = L - 1
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d, 0, 0};
+    if (d <= 1) return f;
+    uint32_t L = 0;
+    while ((1ull << L) < d) ++L;
+    f.mul = (uint32_t)((((1ull << L) - d) << 32) / d + 1);
+    f.shift = L - 1;
+    return f;
+}
+
 template <class K>
 static int occupancy_grid(K kernel, int sm_count, size_t smem) {
     int per_sm = 0;
@@ -432,7 +460,12 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     }
 
     CUDA_TRY(cudaSetDevice(device));
-    ipt_scene* s = new ipt_scene();
+    // owned by `guard` until the very end: every early return below destroys what has been created so far
+    struct SceneGuard {
+        ipt_scene* s;
+        ~SceneGuard() { if (s) ipt_scene_destroy(s); }
+    } guard{new ipt_scene()};
+    ipt_scene* s = guard.s;
     s->device = device;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -501,10 +534,8 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     for (const DevMaterial& m : mats) if (m.ddf != IPT_DDF_COSINE) s->all_lambert = false;
     if (s->mesh) {
         std::string err;
-        if (lbvh_build(desc->triangles, (uint32_t)desc->n_triangles, s->stream, s->bvh, err) != 0) {
-            delete s;
+        if (lbvh_build(desc->triangles, (uint32_t)desc->n_triangles, s->stream, s->bvh, err) != 0)
             return fail(IPT_ERR_CUDA, "LBVH build failed: " + err);
-        }
         dv.n_tris = (uint32_t)desc->n_triangles;
         dv.tri_material = desc->triangle_material;
         dv.tris = s->bvh.tri_records;
@@ -527,10 +558,8 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
                 extra[3 * (size_t)i + 2] = lights[i].weight;
             }
             std::string err;
-            if (lbvh_build(ltris.data(), desc->n_lights, s->stream, s->light_bvh, err, extra.data()) != 0) {
-                delete s;
+            if (lbvh_build(ltris.data(), desc->n_lights, s->stream, s->light_bvh, err, extra.data()) != 0)
                 return fail(IPT_ERR_CUDA, "light LBVH build failed: " + err);
-            }
             dv.light_nodes = s->light_bvh.nodes;
             dv.light_recs = s->light_bvh.tri_records;
             dv.n_light_bvh = desc->n_lights;
@@ -568,6 +597,7 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     s->grid_extend_last = occupancy_grid(k_extend<SP, MS, true>, s->sm_count, sm)
     DISPATCH_SM(s, OCC);
 #undef OCC
+    guard.s = nullptr;
     *out = s;
     return IPT_OK;
 }
@@ -581,7 +611,7 @@ static void free_workspace(Workspace& w) {
 int ipt_scene_destroy(ipt_scene* s) {
     if (!s) return fail(IPT_ERR_INVALID, "null scene");
     cudaSetDevice(s->device);
-    cudaStreamSynchronize(s->stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->host_plane) ipt_plane_destroy(s->host_plane);
     free_workspace(s->ws);
     lbvh_free(s->bvh);
@@ -589,8 +619,10 @@ int ipt_scene_destroy(ipt_scene* s) {
     cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_light_cdf); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
     if (s->pinned) cudaFreeHost(s->pinned);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
-    cudaEventDestroy(s->ev_begin); cudaEventDestroy(s->ev_end);
-    cudaStreamDestroy(s->stream);
+    if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+    if (s->ev_end) cudaEventDestroy(s->ev_end);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError(); // a half-built scene may have tripped an error on the way: it has been reported already
     delete s;
     return IPT_OK;
 }
@@ -749,6 +781,24 @@ int ipt_light_ddf_sample(ipt_scene* s, const float pos[3], uint64_t seed, size_t
     return IPT_OK;
 }
 
+int ipt_philox_batch(int device, const uint32_t* counters, size_t n, uint64_t seed, uint32_t* blocks, float* uniforms) {
+    if (!counters) return fail(IPT_ERR_INVALID, "null argument");
+    if (ipt_device_count() <= device || device < 0) return fail(IPT_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (n == 0) return IPT_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    DevBuf<uint4> d_c, d_b;
+    DevBuf<float4> d_u;
+    CUDA_TRY(d_c.alloc(n)); CUDA_TRY(d_b.alloc(n)); CUDA_TRY(d_u.alloc(n));
+    CUDA_TRY(cudaMemcpy(d_c.p, counters, 16 * n, cudaMemcpyHostToDevice));
+    PhiloxKeys keys;
+    philox_keys(seed, keys);
+    k_philox_batch<<<(unsigned)((n + 255) / 256), 256>>>(d_c.p, n, keys, d_b.p, d_u.p);
+    CUDA_TRY(cudaGetLastError());
+    if (blocks) CUDA_TRY(cudaMemcpy(blocks, d_b.p, 16 * n, cudaMemcpyDeviceToHost));
+    if (uniforms) CUDA_TRY(cudaMemcpy(uniforms, d_u.p, 16 * n, cudaMemcpyDeviceToHost));
+    return IPT_OK;
+}
+
 int ipt_bvh_export(ipt_scene* s, ipt_bvh_node* nodes, uint32_t* sorted_prims, uint64_t* morton, uint64_t* n_nodes) {
     if (!s) return fail(IPT_ERR_INVALID, "null scene");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
@@ -768,14 +818,17 @@ int ipt_bvh_export(ipt_scene* s, ipt_bvh_node* nodes, uint32_t* sorted_prims, ui
 int ipt_plane_create(ipt_scene* s, uint32_t width, uint32_t height, ipt_plane** out) {
     if (!s || !out || !width || !height) return fail(IPT_ERR_INVALID, "bad argument");
     CUDA_TRY(cudaSetDevice(s->device));
+    // one packed block: sum | sumsq | count (12 B per cell), so that the all-reduce and the clear see contiguous memory
+    size_t n = (size_t)width * height;
+    float* block = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&block, 12 * n));
     ipt_plane* p = new ipt_plane();
     p->scene = s; p->width = width; p->height = height; p->owned = true;
-    size_t n = (size_t)width * height;
-    CUDA_TRY(cudaMalloc((void**)&p->sum, 4 * n));
-    CUDA_TRY(cudaMalloc((void**)&p->sumsq, 4 * n));
-    CUDA_TRY(cudaMalloc((void**)&p->count, 4 * n));
+    p->sum = block; p->sumsq = block + n; p->count = reinterpret_cast<uint32_t*>(block + 2 * n);
+    int rc = ipt_plane_clear(p);
+    if (rc) { ipt_plane_destroy(p); return rc; }
     *out = p;
-    return ipt_plane_clear(p);
+    return IPT_OK;
 }
 int ipt_plane_wrap(ipt_scene* s, uint32_t width, uint32_t height, float* d_sum, float* d_sumsq, uint32_t* d_count, ipt_plane** out) {
     if (!s || !out || !width || !height || !d_sum || !d_sumsq || !d_count) return fail(IPT_ERR_INVALID, "bad argument");
@@ -790,9 +843,12 @@ int ipt_plane_clear(ipt_plane* p) {
     std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     CUDA_TRY(cudaSetDevice(p->scene->device));
     size_t n = (size_t)p->width * p->height;
-    CUDA_TRY(cudaMemsetAsync(p->sum, 0, 4 * n, p->scene->stream));
-    CUDA_TRY(cudaMemsetAsync(p->sumsq, 0, 4 * n, p->scene->stream));
-    CUDA_TRY(cudaMemsetAsync(p->count, 0, 4 * n, p->scene->stream));
+    if (p->owned) CUDA_TRY(cudaMemsetAsync(p->sum, 0, 12 * n, p->scene->stream));
+    else {
+        CUDA_TRY(cudaMemsetAsync(p->sum, 0, 4 * n, p->scene->stream));
+        CUDA_TRY(cudaMemsetAsync(p->sumsq, 0, 4 * n, p->scene->stream));
+        CUDA_TRY(cudaMemsetAsync(p->count, 0, 4 * n, p->scene->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(p->scene->stream));
     return IPT_OK;
 }
@@ -820,7 +876,7 @@ int ipt_plane_destroy(ipt_plane* p) {
     if (!p) return fail(IPT_ERR_INVALID, "null plane");
     if (p->owned) {
         cudaSetDevice(p->scene->device);
-        cudaFree(p->sum); cudaFree(p->sumsq); cudaFree(p->count);
+        cudaFree(p->sum); // the packed block
     }
     if (p->scene && p->scene->host_plane == p) p->scene->host_plane = nullptr;
     delete p;
@@ -857,32 +913,48 @@ int ipt_plane_device_ptrs(ipt_plane* p, float** d_sum, float** d_sumsq, uint32_t
     if (d_count) *d_count = p->count;
     return IPT_OK;
 }
-int ipt_plane_allreduce(ipt_plane* p, void* nccl_comm) {
+int ipt_plane_allreduce(ipt_plane* p, void* nccl_comm, float* ms) {
     if (!p || !nccl_comm) return fail(IPT_ERR_INVALID, "null argument");
     std::lock_guard<std::recursive_mutex> lock__(p->scene->mu);
     // ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
     typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    typedef int (*group_fn)(void);
     typedef const char* (*errstr_fn)(int);
     static allreduce_fn all_reduce = nullptr;
+    static group_fn group_start = nullptr, group_end = nullptr;
     static errstr_fn err_string = nullptr;
     if (!all_reduce) {
         void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); // the copy the host application already uses
         if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW);
         if (!h) return fail(IPT_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
-        all_reduce = (allreduce_fn)dlsym(h, "ncclAllReduce");
+        group_start = (group_fn)dlsym(h, "ncclGroupStart");
+        group_end = (group_fn)dlsym(h, "ncclGroupEnd");
         err_string = (errstr_fn)dlsym(h, "ncclGetErrorString");
-        if (!all_reduce) return fail(IPT_ERR_UNSUPPORTED, "ncclAllReduce not found in libnccl");
+        all_reduce = (allreduce_fn)dlsym(h, "ncclAllReduce");
+        if (!all_reduce || !group_start || !group_end) { all_reduce = nullptr; return fail(IPT_ERR_UNSUPPORTED, "ncclAllReduce / ncclGroupStart not found in libnccl"); }
     }
     CUDA_TRY(cudaSetDevice(p->scene->device));
     const size_t n = (size_t)p->width * p->height;
     cudaStream_t st = p->scene->stream;
     const int nccl_float32 = 7, nccl_uint32 = 3, nccl_sum = 0; // nccl.h: ncclFloat32, ncclUint32, ncclSum
-    int rc = all_reduce(p->sum, p->sum, n, nccl_float32, nccl_sum, nccl_comm, st);
-    if (!rc) rc = all_reduce(p->sumsq, p->sumsq, n, nccl_float32, nccl_sum, nccl_comm, st);
-    if (!rc) rc = all_reduce(p->count, p->count, n, nccl_uint32, nccl_sum, nccl_comm, st);
+    CUDA_TRY(cudaEventRecord(p->scene->ev_begin, st));
+    // one grouped launch: the float accumulators (one call when they are contiguous, as in a library-owned plane) + the counters
+    int rc = group_start();
+    if (!rc) {
+        if (p->sumsq == p->sum + n) rc = all_reduce(p->sum, p->sum, 2 * n, nccl_float32, nccl_sum, nccl_comm, st);
+        else {
+            rc = all_reduce(p->sum, p->sum, n, nccl_float32, nccl_sum, nccl_comm, st);
+            if (!rc) rc = all_reduce(p->sumsq, p->sumsq, n, nccl_float32, nccl_sum, nccl_comm, st);
+        }
+        if (!rc) rc = all_reduce(p->count, p->count, n, nccl_uint32, nccl_sum, nccl_comm, st);
+        int rc2 = group_end();
+        if (!rc) rc = rc2;
+    }
     if (rc) return fail(IPT_ERR_CUDA, std::string("ncclAllReduce: ") + (err_string ? err_string(rc) : "error"));
+    CUDA_TRY(cudaEventRecord(p->scene->ev_end, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (ms) CUDA_TRY(cudaEventElapsedTime(ms, p->scene->ev_begin, p->scene->ev_end));
     return IPT_OK;
 }
 int ipt_plane_resolve(ipt_plane* p, float* pixels, uint64_t* pixel_counters, float* max_value) {
@@ -922,21 +994,27 @@ void ipt_render_params_default(ipt_render_params* p) {
     p->plane_mode = IPT_PLANE_GRID;
 }
 
+static size_t workspace_bytes(size_t ray_cap, size_t hit_cap, size_t path_cap, bool two_hit_sets) {
+    return 36 * ray_cap + 32 * std::max<size_t>(hit_cap, 1) * (two_hit_sets ? 2 : 1) + 4 * path_cap;
+}
+// IPT_OK, IPT_ERR_OVERFLOW when the device cannot hold this workspace (the caller retries with a smaller batch), or an error
 static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t path_cap, bool two_hit_sets) {
     Workspace& w = s->ws;
     if (w.ray_cap >= ray_cap && w.hit_cap >= hit_cap && w.path_cap >= path_cap && (w.two_hit_sets || !two_hit_sets)) return IPT_OK;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     free_workspace(w);
-    CUDA_TRY(cudaMalloc((void**)&w.ray_o, 16 * ray_cap));
-    CUDA_TRY(cudaMalloc((void**)&w.ray_d, 16 * ray_cap));
-    CUDA_TRY(cudaMalloc((void**)&w.ray_x, 4 * ray_cap));
-    CUDA_TRY(cudaMalloc((void**)&w.hit_a, 16 * std::max<size_t>(hit_cap, 1)));
-    CUDA_TRY(cudaMalloc((void**)&w.hit_b, 16 * std::max<size_t>(hit_cap, 1)));
-    if (two_hit_sets) {
-        CUDA_TRY(cudaMalloc((void**)&w.hit_a2, 16 * std::max<size_t>(hit_cap, 1)));
-        CUDA_TRY(cudaMalloc((void**)&w.hit_b2, 16 * std::max<size_t>(hit_cap, 1)));
+    void** slots[8] = {(void**)&w.ray_o, (void**)&w.ray_d, (void**)&w.ray_x, (void**)&w.hit_a, (void**)&w.hit_b, (void**)&w.pathval, (void**)&w.hit_a2, (void**)&w.hit_b2};
+    const size_t bytes[8] = {16 * ray_cap, 16 * ray_cap, 4 * ray_cap, 16 * std::max<size_t>(hit_cap, 1), 16 * std::max<size_t>(hit_cap, 1), 4 * path_cap,
+                             16 * std::max<size_t>(hit_cap, 1), 16 * std::max<size_t>(hit_cap, 1)};
+    for (int k = 0; k < (two_hit_sets ? 8 : 6); ++k) {
+        cudaError_t e = cudaMalloc(slots[k], bytes[k]);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            free_workspace(w);
+            return fail(IPT_ERR_OVERFLOW, "the device cannot hold the queue workspace of this batch size");
+        }
+        if (e != cudaSuccess) { free_workspace(w); return fail(IPT_ERR_CUDA, std::string("cudaMalloc (workspace): ") + cudaGetErrorString(e)); }
     }
-    CUDA_TRY(cudaMalloc((void**)&w.pathval, 4 * path_cap));
     w.ray_cap = ray_cap; w.hit_cap = hit_cap; w.path_cap = path_cap; w.two_hit_sets = two_hit_sets;
     return IPT_OK;
 }
@@ -953,6 +1031,9 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     uint32_t tw = p->tile_w ? p->tile_w : p->width, th = p->tile_w ? p->tile_h : p->height;
     if (!tw || !th || tx0 + tw > p->width || ty0 + th > p->height) return fail(IPT_ERR_INVALID, "tile outside the frame");
     if (p->plane_mode > IPT_PLANE_LINEAR) return fail(IPT_ERR_INVALID, "unknown plane mode");
+#ifndef IPT_DEBUG_PRINT
+    if (p->flags & IPT_FLAG_DEBUG_PRINT) return fail(IPT_ERR_UNSUPPORTED, "IPT_FLAG_DEBUG_PRINT needs a library built with -DIPT_DEBUG_PRINT (the device printf is compiled out of the production kernels)");
+#endif
     CUDA_TRY(cudaSetDevice(s->device));
 
     // analytic scenes: the shade kernels trace the children they spawn (FUSE_NEXT / FUSE_LAST in ipt_kernels.cuh)
@@ -988,11 +1069,29 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     uint64_t batch_w = fuse_next ? max_hit_w : max_queued_w;
     uint64_t batch = p->batch_paths ? p->batch_paths : std::min<uint64_t>(1ull << 23, std::max<uint64_t>(1ull << 16, batch_rays / batch_w));
     batch = std::min<uint64_t>(batch, slot_bits >= 32 ? 0xFFFFFFFFull : (1ull << slot_bits));
-    const uint64_t budget = 24ull << 30; // bytes of queue memory
-    while (batch > 1024 && batch * (max_queued_w * 36 + max_hit_w * 32 * (fuse_next ? 2 : 1)) > budget) batch >>= 1;
+    // Queue memory is sized for the worst case of a batch (no overflow path). Budget: IPT_QUEUE_BUDGET_GB (default 24 GiB:
+    // 2^21 paths at 16/8/4/2 need 2 x 8.6 GB of hit records; halving the batch costs ~1.5 %, profiles/tuning_r02.md), never
+    // more than 80 % of what the device has free right now (plus what this scene's workspace already holds), and the
+    // batch is halved again whenever the allocation itself fails.
+    uint64_t budget = 24ull << 30;
+    if (const char* e = std::getenv("IPT_QUEUE_BUDGET_GB")) { double gb = std::atof(e); if (gb > 0) budget = (uint64_t)(gb * (double)(1ull << 30)); }
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const Workspace& w0 = s->ws;
+            uint64_t held = w0.path_cap ? workspace_bytes(w0.ray_cap, w0.hit_cap, w0.path_cap, w0.two_hit_sets) : 0;
+            budget = std::min<uint64_t>(budget, (uint64_t)((double)(free_b + held) * 0.8));
+        } else cudaGetLastError();
+    }
+    while (batch > 1024 && workspace_bytes(batch * max_queued_w, batch * max_hit_w, batch, fuse_next) > budget) batch >>= 1;
     batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(total_paths, 1)));
-    int rc = ensure_workspace(s, batch * max_queued_w, batch * max_hit_w, batch, fuse_next);
-    if (rc) return rc;
+    if ((uint64_t)tw * th + batch > 0xFFFFFFFFull) return fail(IPT_ERR_UNSUPPORTED, "tile too large: tile pixels + batch must stay below 2^32");
+    for (;;) {
+        int rc = ensure_workspace(s, batch * max_queued_w, batch * max_hit_w, batch, fuse_next);
+        if (rc == IPT_OK) break;
+        if (rc != IPT_ERR_OVERFLOW || batch <= 1024) return rc;
+        batch >>= 1; // another tenant (torch, NCCL) took the memory between the query and the allocation
+    }
 
     RenderCtx C;
     std::memset(&C, 0, sizeof C);
@@ -1008,16 +1107,19 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     C.slot_mask = slot_bits >= 32 ? 0xFFFFFFFFu : ((1u << slot_bits) - 1u);
     C.depth_max = p->depth_max;
     std::memcpy(C.schedule, p->schedule, sizeof C.schedule);
-    C.k0 = (uint32_t)p->seed; C.k1 = (uint32_t)(p->seed >> 32);
+    philox_keys(p->seed, C.keys);
+    C.div_tile_pixels = make_fastdiv(C.tile_pixels);
+    C.div_tile_w = make_fastdiv(C.tile_w);
     C.plane_mode = p->plane_mode; C.flags = p->flags;
 
     const bool timing = (p->flags & IPT_FLAG_TIME_KERNELS) != 0;
+    bool timing_failed = false;
     std::vector<int> ev_kind; // 0 generate 1 extend 2 shade 3 accumulate, one entry per bracketed launch
     size_t ev_used = 0;
     auto ev_next = [&]() -> cudaEvent_t {
         if (ev_used == s->events.size()) {
-            cudaEvent_t e;
-            cudaEventCreate(&e);
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) { timing_failed = true; return s->ev_begin; }
             s->events.push_back(e);
         }
         return s->events[ev_used++];
@@ -1029,6 +1131,8 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     uint32_t batches = 0;
     for (uint64_t g0 = 0; g0 < total_paths; g0 += batch, ++batches) {
         C.g0 = g0;
+        C.pass0 = p->pass_begin + (uint32_t)(g0 / C.tile_pixels);
+        C.rem0 = (uint32_t)(g0 % C.tile_pixels);
         C.batch = (uint32_t)std::min<uint64_t>(batch, total_paths - g0);
         CUDA_TRY(cudaMemsetAsync(s->d_cnt, 0, sizeof(uint32_t) * IPT_CNT_WORDS, s->stream));
 #define TIMED(kind, LAUNCH)                                             \
@@ -1061,16 +1165,23 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 TIMED(2, (k_shade<FUSE_NONE, false><<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 continue;
             }
+            // camera rays are traced with the reference's exact arithmetic; rays downstream of a random number with the
+            // contracted form the fused shade kernels use too (so fused and queued runs agree ray for ray)
+            const bool exact_d = d == 0 || !IPT_FAST_SECONDARY;
             if (!traced) { // the rays of this depth wait in the ray queue (depth 0, or an unfused run)
                 if (last) {
                     int g = std::max(1, std::min(s->grid_extend_last, cap_blocks));
-#define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
+#define CALL(SP, MS)                                                                                             \
+    if (MS || exact_d) TIMED(1, (k_extend<SP, MS, true, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d))); \
+    else TIMED(1, (k_extend<SP, false, true, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
                     DISPATCH_SM(s, CALL);
 #undef CALL
                     break;
                 }
                 int g = std::max(1, std::min(s->grid_extend, cap_blocks));
-#define CALL(SP, MS) TIMED(1, (k_extend<SP, MS, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
+#define CALL(SP, MS)                                                                                              \
+    if (MS || exact_d) TIMED(1, (k_extend<SP, MS, false, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d))); \
+    else TIMED(1, (k_extend<SP, false, false, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
                 DISPATCH_SM(s, CALL);
 #undef CALL
             }
@@ -1129,11 +1240,12 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
         stats->nonfinite_dropped = h[ST_DROPPED];
         stats->bvh_nodes_visited = h[ST_NODES];
         stats->triangles_tested = h[ST_TRIS];
-        stats->lights_tested = stats->rays * s->dev.n_lights;
+        stats->lights_tested = h[ST_LIGHTS];
+        stats->light_bvh_nodes_visited = h[ST_LIGHT_NODES];
         stats->batches = batches;
         stats->kernel_launches = launches;
         CUDA_TRY(cudaEventElapsedTime(&stats->ms_total, s->ev_begin, s->ev_end));
-        if (timing) {
+        if (timing && !timing_failed) {
             for (size_t k = 0; k < ev_kind.size(); ++k) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, s->events[2 * k], s->events[2 * k + 1]);

@@ -31,13 +31,16 @@
 #define IPT_EXTEND_MIN_BLOCKS 3
 #endif
 #include <cstdio>
+#ifndef IPT_FAST_SECONDARY
+#define IPT_FAST_SECONDARY 1 // rays of depth >= 1 use the contracted arithmetic (tdot3 / tpoint<false>), see DESIGN.md section 2
+#endif
 
 namespace iptd {
 
 enum LightQuery { LQ_PDF = 0, LQ_NEAREST = 1, LQ_BOTH = 2 };
 
 enum StatSlot {
-    ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED, ST_FUSED,
+    ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED, ST_FUSED, ST_LIGHT_NODES,
     ST_RAYS_AT_DEPTH = 16, // + depth
     ST_COUNT = 16 + IPT_MAX_DEPTH
 };
@@ -66,8 +69,11 @@ struct RenderCtx {
     uint32_t slot_bits, slot_mask;
     uint32_t depth_max;
     uint32_t schedule[IPT_MAX_DEPTH];
-    uint32_t k0, k1; // Philox key
+    PhiloxKeys keys;   // Philox round keys of the seed
     uint32_t plane_mode, flags;
+    // slot -> (pass, loop pixel): g0 = pass0 * tile_pixels + rem0 (host), divisions by launch-constant divisors
+    uint32_t pass0, rem0;
+    FastDiv div_tile_pixels, div_tile_w;
 };
 
 __device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
@@ -98,18 +104,18 @@ __device__ __forceinline__ f3 oct_decode(float ex, float ey) {
 
 // slot -> loop pixel and pass (render_sample's iy/ix loops, main.cpp:189-190)
 __device__ __forceinline__ void slot_to_pixel(const RenderCtx& C, uint32_t slot, uint32_t& ix, uint32_t& iy, uint32_t& pass) {
-    unsigned long long g = C.g0 + slot;
-    uint32_t p = (uint32_t)(g / C.tile_pixels);
-    uint32_t pl = (uint32_t)(g - (unsigned long long)p * C.tile_pixels);
-    uint32_t ty = pl / C.tile_w;
+    uint32_t g = C.rem0 + slot; // < 2^32: ipt_render bounds tile_pixels + batch
+    uint32_t p = fastdiv(g, C.div_tile_pixels);
+    uint32_t pl = g - p * C.tile_pixels;
+    uint32_t ty = fastdiv(pl, C.div_tile_w);
     ix = C.tile_x0 + (pl - ty * C.tile_w);
     iy = C.tile_y0 + ty;
-    pass = C.pass_begin + p;
+    pass = C.pass0 + p;
 }
 
 // jittered sample position (main.cpp:192-198), exact float ops
 __device__ __forceinline__ void jitter_xy(const RenderCtx& C, uint32_t ix, uint32_t iy, uint32_t pass, float& x, float& y) {
-    uint4 r = philox4x32_10(iy * C.width + ix, pass, 0u, 0u, C.k0, C.k1);
+    uint4 r = philox4x32(iy * C.width + ix, pass, 0u, 0u, C.keys);
     x = xdiv(xadd((float)ix, u01(r.x)), (float)C.width);
     y = xdiv(xadd((float)iy, u01(r.y)), (float)C.height);
     if (x == 1.0f) x = __uint_as_float(0x3F7FFFFFu); // nextafter(1.0f, 0.0f)
@@ -144,20 +150,18 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DevSce
 }
 
 // ---- closest hit over the whole scene (Geometry::traceRay) ------------------------------------------
-struct TraceCounters {
-    uint32_t nodes, tris;
-};
 
-template <bool SMALLPT, bool MESH, bool GFAST = false>
+template <bool SMALLPT, bool MESH, bool GFAST = false, bool X = true>
 __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc);
 
 // ---- nearest light (CollectionLighting::traceRayToLight, src/CollectionLighting.cpp:23-34) -----------
-template <bool PDF, bool AREA = false, class LightRef>
+template <bool PDF, bool AREA = false, bool X = true, class LightRef>
 __device__ __forceinline__ void trace_one_light(const LightRef& L, uint32_t i, f3 o, f3 d, bool& any, float& best_len, uint32_t& which, f3& lpos,
                                                 float& lpdf) {
-    LightHit e = light_trace<AREA>(L, o, d);
+    LightHit e = light_trace<AREA, X>(L, o, d);
     if (!e.hit) return;
-    float len = xlength3(xsub3(e.position, o));
+    // X = false: the rays are unit length, so the distance along the ray orders the lights like length(pos - origin) does
+    float len = X ? xlength3(xsub3(e.position, o)) : e.t;
     if (!any || best_len > len) {
         any = true;
         best_len = len;
@@ -181,14 +185,17 @@ __device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, f
 //   LQ_PDF:     the mixture density sum_i w_i * DdfFromLight_i::value(d) over ALL lights the ray hits (ddf.cpp:156-162)
 //   LQ_BOTH:    both from one traversal (returns the density; the nearest hit in which / lpos) — what a traced child ray
 //               needs: its own traceRayToLight and the density of the mixture it was sampled from
+// An LBVH is at most 63 key bits + 32 tie-breaking index bits deep, and the walk pushes one sibling per level.
+#define IPT_LBVH_MAX_HEIGHT 96
 template <int MODE>
-__device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos) {
+__device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& best_len, TraceCounters& tc) {
     constexpr bool NEAREST = MODE != LQ_PDF, PDF = MODE != LQ_NEAREST;
-    float best_len = IPT_INF, pdf_sum = 0.0f;
+    float pdf_sum = 0.0f;
+    best_len = IPT_INF;
     which = IPT_NO_HIT;
     f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     float dlen = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-    uint32_t stack[64];
+    uint32_t stack[IPT_LBVH_MAX_HEIGHT];
     int sp = 0;
     uint32_t node = S.n_light_bvh > 1 ? 0u : 0x80000000u; // a single light is a lone leaf
     while (true) {
@@ -196,6 +203,7 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
             uint32_t pos = node & 0x7FFFFFFFu;
             f8 r0 = ldg256(&S.light_recs[4 * (size_t)pos]);
             f8 r1 = ldg256(&S.light_recs[4 * (size_t)pos + 2]);
+            ++tc.lights;
             f3 corner = mk3(r0.v[0], r0.v[1], r0.v[2]), n = mk3(r0.v[3], r0.v[4], r0.v[5]), rel;
             float t = isect_parallelogram(corner, n, mk3(r0.v[6], r0.v[7], r1.v[0]), mk3(r1.v[1], r1.v[2], r1.v[3]), r1.v[5] != 0.0f, o, d, &rel);
             if (t != IPT_INF) {
@@ -216,6 +224,7 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
         } else {
             f8 n0 = ldg256(&S.light_nodes[node]);
             f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[node]) + 32);
+            ++tc.light_nodes;
             // entry distances are in units of t; a hit at length L has t = L / |d|
             float limit = MODE == LQ_NEAREST ? (best_len / dlen) * 1.0001f + 1e-6f : IPT_INF;
             bool h0 = light_box(n0, 0, o, inv, limit), h1 = light_box(n1, 0, o, inv, limit);
@@ -230,7 +239,7 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
             node = stack[--sp];
         }
     }
-    return PDF ? pdf_sum : best_len;
+    return pdf_sum;
 }
 
 // nearest light, scanning in list order with strict `>` (CollectionLighting.cpp:23-34); `lpdf` receives the light part
@@ -259,23 +268,27 @@ __device__ __forceinline__ float light_power(const DevScene& S, uint32_t i) {
     float power = lights_inline<SPEC>(S) ? S.lights[i].surface_power : S.lights_g[i].surface_power;
     return isfinite(power) ? power : 1.0f; // main.cpp:123 point-light hack
 }
-template <bool PDF = true, int SPEC = SPEC_RUNTIME>
-__device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& lpdf) {
+// `ldist` receives the nearest light's distance: length(pos - origin) as CollectionLighting.cpp:27 computes it, or — for
+// the contracted secondary-ray form (X = false) of the inline / linear scans — the distance along the unit direction.
+template <bool PDF = true, int SPEC = SPEC_RUNTIME, bool X = true>
+__device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& lpdf, float& ldist, TraceCounters& tc) {
     bool any = false;
-    float best_len = 0.0f;
+    ldist = 0.0f;
     lpdf = 0.0f;
     if (has_light_bvh<SPEC>(S)) {
-        if (PDF) lpdf = light_bvh_query<LQ_BOTH>(S, o, d, which, lpos);
-        else light_bvh_query<LQ_NEAREST>(S, o, d, which, lpos);
+        if (PDF) lpdf = light_bvh_query<LQ_BOTH>(S, o, d, which, lpos, ldist, tc);
+        else light_bvh_query<LQ_NEAREST>(S, o, d, which, lpos, ldist, tc);
         return which != IPT_NO_HIT;
     }
     if (SPEC == SPEC_LIGHT_BVH) return false; // unreachable: the LBVH branch above always returns
     if (lights_inline<SPEC>(S)) {
 #pragma unroll
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i) // static indices: light constants become immediate constant-bank operands
-            if (i < (int)S.n_lights) trace_one_light<PDF, IPT_SPEC_AREA_LIGHTS(SPEC)>(S.lights[i], i, o, d, any, best_len, which, lpos, lpdf);
+            if (i < (int)S.n_lights) trace_one_light<PDF, IPT_SPEC_AREA_LIGHTS(SPEC), X>(S.lights[i], i, o, d, any, ldist, which, lpos, lpdf);
+        tc.lights += min(S.n_lights, (uint32_t)IPT_INLINE_LIGHTS);
     } else if (!IPT_SPEC_INLINE_LIGHTS(SPEC)) {
-        for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light<PDF>(S.lights_g[i], i, o, d, any, best_len, which, lpos, lpdf);
+        for (uint32_t i = 0; i < S.n_lights; ++i) trace_one_light<PDF, false, X>(S.lights_g[i], i, o, d, any, ldist, which, lpos, lpdf);
+        tc.lights += S.n_lights;
     }
     return any;
 }
@@ -288,25 +301,25 @@ struct Outcome {
     float light_pdf; // light part of the mixture density along the ray (see trace_lights)
 };
 
+// main.cpp:113: the light wins if there is no surface hit or the surface point is farther than the light's
+template <bool X>
+__device__ __forceinline__ bool light_nearer(const SurfHit& sh, f3 o, f3 d, float ldist) {
+    if (sh.prim == IPT_NO_HIT) return true;
+    if (!X) return sh.t > ldist; // unit direction: the distances along the ray compare like the lengths
+    return xlength3(xsub3(xpoint(o, d, sh.t), o)) > ldist;
+}
+
 // Geometry::traceRay + Lighting::traceRayToLight + the decision of main.cpp:111-128
-template <bool SMALLPT, bool MESH, int SPEC = SPEC_RUNTIME>
+template <bool SMALLPT, bool MESH, int SPEC = SPEC_RUNTIME, bool X = true>
 __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
-    r.surf = trace_geometry<SMALLPT, MESH, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, tc);
+    r.surf = trace_geometry<SMALLPT, MESH, IPT_SPEC_FAST_GEOMETRY(SPEC), X>(S, o, d, tc);
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
-    bool lh = trace_lights<true, SPEC>(S, o, d, r.light, r.light_pos, r.light_pdf);
-    bool sh = r.surf.prim != IPT_NO_HIT;
-    r.kind = 0;
-    if (lh) {
-        bool light_wins = !sh;
-        if (sh) {
-            f3 sp = xpoint(o, d, r.surf.t);
-            light_wins = xlength3(xsub3(sp, o)) > xlength3(xsub3(r.light_pos, o));
-        }
-        if (light_wins) { r.kind = 2; return r; }
-    }
-    if (sh) r.kind = 1;
+    float ldist;
+    bool lh = trace_lights<true, SPEC, X>(S, o, d, r.light, r.light_pos, r.light_pdf, ldist, tc);
+    r.kind = r.surf.prim != IPT_NO_HIT ? 1u : 0u;
+    if (lh && light_nearer<X>(r.surf, o, d, ldist)) r.kind = 2;
     return r;
 }
 
@@ -314,23 +327,18 @@ __device__ __forceinline__ Outcome trace_scene(const DevScene& S, f3 o, f3 d, Tr
 // a light before any surface. Lights are tested first and the geometry only for rays that hit one ("shadow ray"):
 // the decision is the same expression as in trace_scene, evaluated for fewer rays. kind 3 = no light along the ray
 // (surface or miss, not resolved).
-template <bool SMALLPT, bool MESH, int SPEC = SPEC_RUNTIME>
+template <bool SMALLPT, bool MESH, int SPEC = SPEC_RUNTIME, bool X = true>
 __device__ __forceinline__ Outcome trace_scene_last(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     Outcome r;
     r.light = IPT_NO_HIT;
     r.light_pos = mk3(0, 0, 0);
     r.surf.prim = IPT_NO_HIT; r.surf.t = IPT_INF; r.surf.tri_pos = IPT_NO_HIT;
-    bool lh = trace_lights<true, SPEC>(S, o, d, r.light, r.light_pos, r.light_pdf);
+    float ldist;
+    bool lh = trace_lights<true, SPEC, X>(S, o, d, r.light, r.light_pos, r.light_pdf, ldist, tc);
     r.kind = 3;
     if (!lh) return r;
-    r.surf = trace_geometry<SMALLPT, MESH, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, tc);
-    bool sh = r.surf.prim != IPT_NO_HIT;
-    bool light_wins = !sh;
-    if (sh) {
-        f3 sp = xpoint(o, d, r.surf.t);
-        light_wins = xlength3(xsub3(sp, o)) > xlength3(xsub3(r.light_pos, o));
-    }
-    r.kind = light_wins ? 2u : 1u;
+    r.surf = trace_geometry<SMALLPT, MESH, IPT_SPEC_FAST_GEOMETRY(SPEC), X>(S, o, d, tc);
+    r.kind = light_nearer<X>(r.surf, o, d, ldist) ? 2u : 1u;
     return r;
 }
 
@@ -349,14 +357,15 @@ __device__ __forceinline__ void flush_stat(unsigned long long* stats, int slot, 
 
 // K2 extend: one thread per ray of depth `depth`. Light hits are accumulated here (the emission is the leaf
 // of the estimator tree); surface hits are compacted into the hit queue unless this is the last traced depth.
-template <bool SMALLPT, bool MESH, bool LAST>
+// X: exact arithmetic (the camera rays, depth 0) or the contracted secondary-ray form (depth > 0; never with MESH)
+template <bool SMALLPT, bool MESH, bool LAST, bool X = true>
 __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t n_surface = 0, n_light = 0, n_miss = 0, n_dropped = 0;
-    TraceCounters tc{0, 0};
+    TraceCounters tc{0, 0, 0, 0};
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
         uint32_t i = base + lane;
         bool active = i < n;
@@ -368,13 +377,15 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
             rd = C.ray_d[i];
             float sv = C.ray_x[i];
             f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
-            if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) oc = trace_scene_last<SMALLPT, MESH>(S, o, d, tc);
-            else oc = trace_scene<SMALLPT, MESH>(S, o, d, tc);
+            if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) oc = trace_scene_last<SMALLPT, MESH, SPEC_RUNTIME, X>(S, o, d, tc);
+            else oc = trace_scene<SMALLPT, MESH, SPEC_RUNTIME, X>(S, o, d, tc);
             ro.w = resolve_weight(S, ro.w, sv, oc.light_pdf);
             if (!isfinite(ro.w)) { ++n_dropped; oc.kind = 4; } // non-finite multiplier (main.cpp:175): drop this sample
-            if (C.flags & 4u)
+#ifdef IPT_DEBUG_PRINT
+            if (C.flags & IPT_FLAG_DEBUG_PRINT)
                 printf("GPU extend d=%u node=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) thr=%.9g kind=%u prim=%u t=%.9g\n", depth,
                        C.slot_bits == 32 ? 0u : (__float_as_uint(rd.w) >> C.slot_bits), o.x, o.y, o.z, d.x, d.y, d.z, ro.w, oc.kind, oc.surf.prim, oc.surf.t);
+#endif
             if (oc.kind == 2) {
                 ++n_light;
                 float power = S.light_inline ? S.lights[oc.light].surface_power : S.lights_g[oc.light].surface_power;
@@ -414,6 +425,8 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
         flush_stat(C.stats, ST_NODES, tc.nodes);
         flush_stat(C.stats, ST_TRIS, tc.tris);
     }
+    flush_stat(C.stats, ST_LIGHTS, tc.lights);
+    flush_stat(C.stats, ST_LIGHT_NODES, tc.light_nodes);
 }
 
 // geometric normal + material of a hit primitive (GeometrySphereInBox.cpp:43-56 and the other geometries)
@@ -446,21 +459,16 @@ __device__ __forceinline__ void surface_frame(const DevScene& S, uint32_t prim, 
 #endif
 // Second half of trace_scene_last for a parked ray that reached a light at `lpos`: Geometry::traceRay and the
 // light-vs-surface decision of main.cpp:113; the light's contribution is added if nothing is nearer.
-template <bool SMALLPT, int SPEC>
+template <bool SMALLPT, int SPEC, bool X>
 __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, TraceCounters& tc,
                                                uint32_t& n_light, uint32_t& n_surface) {
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
-    f3 lpos = mk3(dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], dq[8 * IPT_PARK + k]);
-    SurfHit sh = trace_geometry<SMALLPT, false, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, tc);
-    bool light_wins = sh.prim == IPT_NO_HIT;
-    if (!light_wins) {
-        f3 sp = xpoint(o, d, sh.t);
-        light_wins = xlength3(xsub3(sp, o)) > xlength3(xsub3(lpos, o));
-    }
-    if (light_wins) {
+    float ldist = dq[6 * IPT_PARK + k];
+    SurfHit sh = trace_geometry<SMALLPT, false, IPT_SPEC_FAST_GEOMETRY(SPEC), X>(S, o, d, tc);
+    if (light_nearer<X>(sh, o, d, ldist)) {
         ++n_light;
-        atomicAdd(&C.pathval[__float_as_uint(dq[10 * IPT_PARK + k])], dq[9 * IPT_PARK + k]);
+        atomicAdd(&C.pathval[__float_as_uint(dq[8 * IPT_PARK + k])], dq[7 * IPT_PARK + k]);
     } else ++n_surface;
 }
 
@@ -474,19 +482,17 @@ __device__ __forceinline__ bool light_root_hit(const DevScene& S, f3 o, f3 d) {
 // Many-light scenes, last traced depth: the whole of trace_scene_last for a parked ray (light LBVH walk, weight, and the
 // occlusion test if a light was reached). Parked are only rays that passed light_root_hit, so the lanes of a pop walk
 // the LBVH together instead of idling next to the rays that leave at the root.
-template <bool SMALLPT>
+template <bool SMALLPT, bool X>
 __device__ __forceinline__ void last_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, TraceCounters& tc,
                                             uint32_t& n_light, uint32_t& n_surface, uint32_t& n_dropped) {
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
-    Outcome oc = trace_scene_last<SMALLPT, false, SPEC_LIGHT_BVH>(S, o, d, tc);
+    Outcome oc = trace_scene_last<SMALLPT, false, SPEC_LIGHT_BVH, X>(S, o, d, tc);
     float wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
     if (!isfinite(wr)) ++n_dropped;
     else if (oc.kind == 2) {
         ++n_light;
-        float power = S.light_inline ? S.lights[oc.light].surface_power : S.lights_g[oc.light].surface_power;
-        if (!isfinite(power)) power = 1.0f; // main.cpp:123 point-light hack
-        atomicAdd(&C.pathval[__float_as_uint(dq[10 * IPT_PARK + k])], wr * power);
+        atomicAdd(&C.pathval[__float_as_uint(dq[8 * IPT_PARK + k])], wr * light_power<SPEC_LIGHT_BVH>(S, oc.light));
     } else if (oc.kind == 1) ++n_surface;
 }
 
@@ -496,7 +502,7 @@ struct ExtendCounters {
 // The body of k_extend<.., LAST = false> for one parked child ray of depth `depth` (entry k of the warp's queue; all 32
 // lanes call this, `valid` masks the drain): trace_scene, weight resolution, emission, and the warp-aggregated append
 // of the surface hits to the hit set of `depth`.
-template <bool SMALLPT, int SPEC>
+template <bool SMALLPT, int SPEC, bool X>
 __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, bool valid, uint32_t depth,
                                               TraceCounters& tc, ExtendCounters& ec) {
     const uint32_t lane = threadIdx.x & 31;
@@ -509,7 +515,7 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
         o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
         d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
         ctag = __float_as_uint(dq[8 * IPT_PARK + k]);
-        oc = trace_scene<SMALLPT, false, SPEC>(S, o, d, tc);
+        oc = trace_scene<SMALLPT, false, SPEC, X>(S, o, d, tc);
         wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
         if (!isfinite(wr)) ++ec.dropped; // non-finite multiplier (main.cpp:175): drop this sample
         else if (oc.kind == 2) {
@@ -556,9 +562,13 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
     uint32_t n_failed = 0, n_pruned = 0, n_dropped = 0;
     uint32_t n_fused = 0, n_light = 0, n_surface = 0;
     ExtendCounters ec{0, 0, 0, 0};
-    TraceCounters tc{0, 0};
-    __shared__ float dq_all[FUSE != FUSE_NONE ? (256 / 32) * 11 * IPT_PARK : 1];
-    float* dq = dq_all + (FUSE != FUSE_NONE ? (threadIdx.x >> 5) * 11 * IPT_PARK : 0); // this warp's parked rays
+    TraceCounters tc{0, 0, 0, 0};
+    // every ray traced here is downstream of a random number (depth >= 1): the contracted secondary-ray arithmetic, the
+    // same k_extend<.., X = false> uses for queued rays of depth > 0
+    constexpr bool X = !IPT_FAST_SECONDARY;
+    constexpr int PARK_WORDS = 9;
+    __shared__ float dq_all[FUSE != FUSE_NONE ? (256 / 32) * PARK_WORDS * IPT_PARK : 1];
+    float* dq = dq_all + (FUSE != FUSE_NONE ? (threadIdx.x >> 5) * PARK_WORDS * IPT_PARK : 0); // this warp's parked rays
     uint32_t qn = 0;                                                            // warp-uniform
     uint32_t* out_count = &C.cnt[2 * (depth + 1)];
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
@@ -601,10 +611,12 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             float wgt = 0.0f, child_sv = -1.0f;
             uint32_t child = node * n_children + c;
             if (active) {
-                uint4 r = philox4x32_10(pixel, pass, child, depth + 1, C.k0, C.k1);
+                uint4 r = philox4x32(pixel, pass, child, depth + 1, C.keys);
                 w = mix_sample<IPT_SPEC_INLINE_LIGHTS(SPEC), IPT_SPEC_AREA_LIGHTS(SPEC), SPEC == SPEC_LAMBERT_BOX>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
-                    if (FUSE == FUSE_NONE && (C.flags & 4u)) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
+#ifdef IPT_DEBUG_PRINT
+                    if (FUSE == FUSE_NONE && (C.flags & IPT_FLAG_DEBUG_PRINT)) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));
+#endif
                     ++n_failed; // still counted in the 1/n divisor (main.cpp:161-163,181)
                 } else {
                     float sv = sdf_value<SPEC == SPEC_LAMBERT_BOX>(sdf, w);
@@ -632,7 +644,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     __syncwarp();
                     if (qn >= 32) {
                         qn -= 32;
-                        extend_parked<SMALLPT, SPEC>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
+                        extend_parked<SMALLPT, SPEC, X>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
                         __syncwarp();
                     }
                 }
@@ -657,26 +669,26 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                             dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
                             dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
                             dq[6 * IPT_PARK + k] = wgt; dq[7 * IPT_PARK + k] = child_sv;
-                            dq[10 * IPT_PARK + k] = __uint_as_float(tag & C.slot_mask);
+                            dq[8 * IPT_PARK + k] = __uint_as_float(tag & C.slot_mask);
                         }
                         qn += __popc(pbb);
                         __syncwarp();
                         if (qn >= 32) {
                             qn -= 32;
-                            last_parked<SMALLPT>(S, C, dq, qn + lane, tc, n_light, n_surface, n_dropped);
+                            last_parked<SMALLPT, X>(S, C, dq, qn + lane, tc, n_light, n_surface, n_dropped);
                             __syncwarp();
                         }
                     }
                     continue;
                 }
                 bool park = false;
-                float contrib = 0.0f;
-                f3 lpos = mk3(0, 0, 0);
+                float contrib = 0.0f, ldist = 0.0f;
                 if (emit) {
                     ++n_fused;
                     uint32_t li = IPT_NO_HIT;
                     float lpdf;
-                    bool lh = trace_lights<true, SPEC == SPEC_LIGHT_BVH ? SPEC_FEW_LIGHTS : SPEC>(S, pos, w, li, lpos, lpdf);
+                    f3 lpos;
+                    bool lh = trace_lights<true, SPEC == SPEC_LIGHT_BVH ? SPEC_FEW_LIGHTS : SPEC, X>(S, pos, w, li, lpos, lpdf, ldist, tc);
                     float wr = resolve_weight(S, wgt, child_sv, lpdf);
                     if (!isfinite(wr)) ++n_dropped;
                     else if (lh) {
@@ -690,14 +702,13 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                         uint32_t k = qn + __popc(pb & ((1u << lane) - 1u));
                         dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
                         dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
-                        dq[6 * IPT_PARK + k] = lpos.x; dq[7 * IPT_PARK + k] = lpos.y; dq[8 * IPT_PARK + k] = lpos.z;
-                        dq[9 * IPT_PARK + k] = contrib; dq[10 * IPT_PARK + k] = __uint_as_float(tag & C.slot_mask);
+                        dq[6 * IPT_PARK + k] = ldist; dq[7 * IPT_PARK + k] = contrib; dq[8 * IPT_PARK + k] = __uint_as_float(tag & C.slot_mask);
                     }
                     qn += __popc(pb);
                     __syncwarp();
                     if (qn >= 32) {
                         qn -= 32;
-                        resolve_parked<SMALLPT, SPEC>(S, C, dq, qn + lane, tc, n_light, n_surface);
+                        resolve_parked<SMALLPT, SPEC, X>(S, C, dq, qn + lane, tc, n_light, n_surface);
                         __syncwarp();
                     }
                 }
@@ -720,10 +731,10 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
         }
     }
     if (FUSE == FUSE_LAST && lane < qn) { // drain
-        if (has_light_bvh<SPEC>(S)) last_parked<SMALLPT>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
-        else resolve_parked<SMALLPT, SPEC>(S, C, dq, lane, tc, n_light, n_surface);
+        if (has_light_bvh<SPEC>(S)) last_parked<SMALLPT, X>(S, C, dq, lane, tc, n_light, n_surface, n_dropped);
+        else resolve_parked<SMALLPT, SPEC, X>(S, C, dq, lane, tc, n_light, n_surface);
     }
-    if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT, SPEC>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
+    if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT, SPEC, X>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
     n_light += ec.light; n_surface += ec.surface; n_dropped += ec.dropped;
     flush_stat(C.stats, ST_FAILED, n_failed);
     flush_stat(C.stats, ST_PRUNED, n_pruned);
@@ -732,6 +743,8 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
         flush_stat(C.stats, ST_LIGHT, n_light);
         flush_stat(C.stats, ST_SURFACE, n_surface);
         flush_stat(C.stats, ST_MISS, ec.miss);
+        flush_stat(C.stats, ST_LIGHTS, tc.lights);
+        flush_stat(C.stats, ST_LIGHT_NODES, tc.light_nodes);
         // rays of depth+1 that were traced without being queued: k_accumulate folds cnt[] into the per-depth ray counts
         for (int off = 16; off > 0; off >>= 1) n_fused += __shfl_down_sync(0xffffffffu, n_fused, off);
         if (lane == 0 && n_fused) {

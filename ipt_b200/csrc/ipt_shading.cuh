@@ -14,18 +14,6 @@ namespace iptd {
 
 #define IPT_PI_F 3.14159265358979323846f
 
-// SFU square root / reciprocal (sqrt.approx / rcp.approx, ~1 ulp): sampling code only, never the exact routines
-__device__ __forceinline__ float fsqrt(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float frcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 // The sampling code spells out its multiply-adds (__fmaf_rn / __fmul_rn / ...): left to the compiler, the contraction
 // of a*b + c into an FMA depends on the surrounding code, so the SAME source gave directions differing in the last bit
 // between the instantiations of k_shade — harmless statistically, but then "fused" and "queued" runs could not be
@@ -224,7 +212,7 @@ __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float 
 }
 
 template <int MODE>
-__device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos); // ipt_kernels.cuh
+__device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& best_len, TraceCounters& tc); // ipt_kernels.cuh
 
 // UnionDdf::value over [lights..., sdf] (src/libddf/ddf.cpp:156-162) with the weights of main.cpp:143
 __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3 pos, f3 w, float sdf_val) {
@@ -236,7 +224,9 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
     } else if (S.n_light_bvh) {
         uint32_t which;
         f3 lpos;
-        lp = light_bvh_query<0 /* LQ_PDF */>(S, pos, w, which, lpos);
+        float best_len;
+        TraceCounters tc{0, 0, 0, 0};
+        lp = light_bvh_query<0 /* LQ_PDF */>(S, pos, w, which, lpos, best_len, tc);
     } else {
         for (uint32_t i = 0; i < S.n_lights; ++i) {
             const DevLight& L = S.lights_g[i];

@@ -118,13 +118,15 @@ extern __shared__ uint32_t ipt_dyn_smem[];
 // generic ordered scan
 // GFAST: the caller knows at compile time that the scene takes the first branch all the way (grouped planes and
 // inline spheres only), so none of the generic scans is instantiated
-template <bool SMALLPT, bool GFAST = false>
+// X = false: contracted arithmetic in the grouped-plane / inline-sphere branch (secondary rays, see ipt_device.cuh); the
+// generic ordered scans keep the exact routines
+template <bool SMALLPT, bool GFAST = false, bool X = true>
 __device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, double& dist_d, float& dist_f, uint32_t& best) {
     if (GFAST || (!SMALLPT && S.planes_grouped)) {
         if (S.n_planes) {
-            isect_axis_planes(S.plane_of[0], S.plane_of[1], o.x, d.x, o, d, dist_f, best);
-            isect_axis_planes(S.plane_of[2], S.plane_of[3], o.y, d.y, o, d, dist_f, best);
-            isect_axis_planes(S.plane_of[4], S.plane_of[5], o.z, d.z, o, d, dist_f, best);
+            isect_axis_planes<X, 0>(S.plane_of[0], S.plane_of[1], o.x, d.x, o, d, dist_f, best);
+            isect_axis_planes<X, 1>(S.plane_of[2], S.plane_of[3], o.y, d.y, o, d, dist_f, best);
+            isect_axis_planes<X, 2>(S.plane_of[4], S.plane_of[5], o.z, d.z, o, d, dist_f, best);
         }
         if (GFAST || S.others_inline) {
             // static indices: every sphere constant is an immediate constant-bank operand, no indexed LDC
@@ -132,7 +134,7 @@ __device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, 
             for (int k = 0; k < IPT_INLINE_OTHERS; ++k) {
                 if (k < (int)S.n_others) {
                     const DevSphere& sp = S.others[k];
-                    float t = isect_sphere(sp.r2, xsub3(o, mk3(sp.cx, sp.cy, sp.cz)), d);
+                    float t = isect_sphere<X>(sp.r2, xsub3(o, mk3(sp.cx, sp.cy, sp.cz)), d);
                     if (t < dist_f || (t == dist_f && t != IPT_INF && sp.index < best)) { dist_f = t; best = sp.index; }
                 }
             }
@@ -146,12 +148,12 @@ __device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, 
     }
 }
 
-template <bool SMALLPT, bool MESH, bool GFAST>
+template <bool SMALLPT, bool MESH, bool GFAST, bool X>
 __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     double dist_d = (double)IPT_INF;
     float dist_f = IPT_INF;
     uint32_t best = IPT_NO_HIT;
-    analytic_closest<SMALLPT, GFAST>(S, o, d, dist_d, dist_f, best);
+    analytic_closest<SMALLPT, GFAST, X>(S, o, d, dist_d, dist_f, best);
     SurfHit r;
     r.prim = best;
     r.tri_pos = IPT_NO_HIT;
@@ -201,11 +203,11 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t n_surface = 0, n_light = 0, n_miss = 0, n_dropped = 0;
-    TraceCounters tc{0, 0};
+    TraceCounters tc{0, 0, 0, 0};
     bool have = false, trav = false, exhausted = false;
     float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
     f3 inv = mk3(0, 0, 0), lpos = mk3(0, 0, 0);
-    float a_t = IPT_INF, best_t = IPT_INF, sv = -1.0f;
+    float a_t = IPT_INF, best_t = IPT_INF, sv = -1.0f, ldist = 0.0f;
     uint32_t a_prim = IPT_NO_HIT, best_orig = IPT_NO_HIT, best_pos = IPT_NO_HIT, lwhich = IPT_NO_HIT, node = 0, pend = IPT_NO_HIT;
     TravStack st;
     st.sm = ipt_dyn_smem + threadIdx.x;
@@ -229,9 +231,9 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                     lwhich = IPT_NO_HIT;
                     float lpdf;
                     if (lights_inline<SPEC>(S)) {
-                        go = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf); // density from lpos when the ray is finalised
+                        go = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc); // density from lpos when the ray is finalised
                     } else {
-                        go = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf);
+                        go = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc);
                         ro.w = resolve_weight(S, ro.w, sv, lpdf); // resolved now: no density register lives through the traversal
                         sv = -1.0f;
                     }
@@ -320,25 +322,28 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
             if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) lh = true;
             else {
                 lwhich = IPT_NO_HIT;
-                if (lights_inline<SPEC>(S)) lh = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf);
-                else lh = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf);
+                if (lights_inline<SPEC>(S)) lh = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc);
+                else lh = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc);
             }
             // single inline light: its density follows from the hit position that is kept anyway
             if (lights_inline<SPEC>(S) && lh && S.n_lights) lpdf = S.lights[0].weight * light_pdf_at<IPT_SPEC_AREA_LIGHTS(SPEC)>(S.lights[0], o, lpos);
             bool sh = prim != IPT_NO_HIT;
+#ifdef IPT_DEBUG_PRINT
             float K = ro.w;
+#endif
             ro.w = resolve_weight(S, ro.w, sv, lpdf);
-            if (C.flags & 4u)
+#ifdef IPT_DEBUG_PRINT
+            if (C.flags & IPT_FLAG_DEBUG_PRINT)
                 printf("GPU mesh extend d=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) K=%.9g sv=%.9g thr=%.9g lh=%d lpos=(%.9g %.9g %.9g) prim=%u t=%.9g\n", depth, o.x, o.y, o.z,
                        d.x, d.y, d.z, K, sv, ro.w, (int)lh, lpos.x, lpos.y, lpos.z, prim, t);
+#endif
             if (!isfinite(ro.w)) {
                 ++n_dropped; // non-finite multiplier (main.cpp:175): drop this sample
             } else {
                 bool light_wins = false;
                 if (lh) {
-                    float len_light = xlength3(xsub3(lpos, o));
                     float len_surf = sh ? xlength3(xsub3(xpoint(o, d, t), o)) : IPT_INF;
-                    light_wins = !sh || len_surf > len_light; // main.cpp:113
+                    light_wins = !sh || len_surf > ldist; // main.cpp:113 (ldist = length(light position - origin))
                 }
                 if (light_wins) {
                     ++n_light;
@@ -375,6 +380,8 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
     flush_stat(C.stats, ST_DROPPED, n_dropped);
     flush_stat(C.stats, ST_NODES, tc.nodes);
     flush_stat(C.stats, ST_TRIS, tc.tris);
+    flush_stat(C.stats, ST_LIGHTS, tc.lights);
+    flush_stat(C.stats, ST_LIGHT_NODES, tc.light_nodes);
 }
 
 } // namespace iptd

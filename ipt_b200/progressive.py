@@ -22,18 +22,24 @@ KEY_LEFT, KEY_RIGHT, KEY_DOWN, KEY_UP = 0, 1, 2, 3
 class ProgressiveSession:
     def __init__(self, scene_name: str = "box", width: int = 640, height: int = 640, passes_per_call: int = 4, seed: int = 0,
                  depth_max: int = 4, schedule=(16, 8, 4, 2), glare_cutoff: float = 1.01, device: int = 0, checkpoint_path=None):
+        self.scene_name = scene_name
         self.description = capi.SceneDescription(scene_name)
         self.scene = capi.Scene(self.description, device)
         self.plane = capi.Plane(self.scene, width, height)
         self.camera = copy.copy(self.description.desc.camera)
         self.width, self.height, self.passes_per_call, self.seed = width, height, passes_per_call, seed
         self.depth_max, self.schedule, self.glare_cutoff = depth_max, list(schedule), glare_cutoff  # gui.h:24 default cutoff
-        self.checkpoint_path = checkpoint_path
+        self.checkpoint_path = str(checkpoint.normalise(checkpoint_path)) if checkpoint_path else None
         self.next_pass = 0      # passes accumulated in the plane for the CURRENT camera start at `first_pass`
         self.first_pass = 0
         self.rays = 0
-        if checkpoint_path and os.path.exists(checkpoint_path):
-            self.resume(checkpoint_path)
+        if self.checkpoint_path and os.path.exists(self.checkpoint_path):
+            self.resume(self.checkpoint_path)
+
+    def identity(self) -> dict:
+        """What a checkpoint must agree on to be resumed by this session (the estimator and its frame)."""
+        return dict(scene=self.scene_name, depth_max=self.depth_max, schedule=list(self.schedule), plane_mode=capi.PLANE_GUI,
+                    passes_per_call=self.passes_per_call)
 
     # -- main.cpp:262-268: one iteration of thread_func (passes_per_call samples per pixel instead of one)
     def step(self, calls: int = 1):
@@ -80,11 +86,11 @@ class ProgressiveSession:
     def checkpoint(self, path=None):
         path = path or self.checkpoint_path
         cam = [list(self.camera.position), list(self.camera.direction), list(self.camera.right), list(self.camera.up)]
-        checkpoint.save(path, self.plane, self.next_pass, self.seed, first_pass=self.first_pass, camera=cam, rays=self.rays,
-                        glare_cutoff=self.glare_cutoff)
+        return checkpoint.save(path, self.plane, self.next_pass, self.seed, identity=self.identity(), first_pass=self.first_pass,
+                               camera=cam, rays=self.rays, glare_cutoff=self.glare_cutoff)
 
     def resume(self, path=None):
-        meta = checkpoint.load(path or self.checkpoint_path, self.plane)
+        meta = checkpoint.load(path or self.checkpoint_path, self.plane, identity=self.identity())
         self.next_pass, self.first_pass = int(meta["next_pass"]), int(meta["first_pass"])
         self.seed, self.rays, self.glare_cutoff = int(meta["seed"]), int(meta["rays"]), float(meta["glare_cutoff"])
         cam = meta["camera"]

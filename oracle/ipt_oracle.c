@@ -82,8 +82,9 @@ static float randf_drand48(void) {
     return res;
 }
 
-static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-    for (int r = 0; r < 10; ++r) {
+/* Philox4x32-R (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC11), the published algorithm */
+static void philox4x32_r(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -95,7 +96,10 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-static inline float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    philox4x32_r(IPT_PHILOX_ROUNDS, c0, c1, c2, c3, k0, k1, out); /* the render's stream (name kept from the 10-round default) */
+}
+static inline float u01(uint32_t x) { return (float)(x >> (32 - IPT_U01_BITS)) * (1.0f / (float)(1u << IPT_U01_BITS)); }
 
 /* One tree node's draws. DRAND48: sequential. PHILOX: out[role] of counter (pixel, pass, node, depth). */
 typedef struct {
@@ -910,6 +914,9 @@ int ipt_oracle_light_fields(const ipt_scene_desc* desc, uint32_t i, float* out5)
 }
 
 /* Philox known-answer access for tests */
+void ipt_oracle_philox_rounds(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+    philox4x32_r(rounds, c0, c1, c2, c3, k0, k1, out);
+}
 void ipt_oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
     philox4x32_10(c0, c1, c2, c3, k0, k1, out);
 }

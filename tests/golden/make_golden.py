@@ -27,14 +27,19 @@ HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
 sys.path.insert(0, str(HERE.parent.parent))
 
-IMAGE_JOBS = {  # scene: (W, H, passes)
-    "box": (128, 128, 256),
-    "cornell": (128, 128, 256),
-    "corner": (64, 64, 128),
-    "openspheres": (64, 64, 128),
-    # high-spp goldens for the "image relative RMSE below 1 % at high spp" bar of BASELINE.json
-    "box@hi": (64, 64, 2048),
-    "cornell@hi": (64, 64, 2048),
+IMAGE_JOBS = {  # scene: (W, H, passes). 2048 passes: SURVEY 8d's tolerances (99.7 % within 3 sigma, |mean z| < 0.1, block relRMSE
+    # < 1 %) need a golden whose own noise is well below them; the sizes keep each job to a few minutes on 8 cores.
+    "box": (96, 96, 2048),
+    "cornell": (96, 96, 2048),
+    "corner": (96, 96, 2048),
+    "openspheres": (96, 96, 2048),
+    "fractal": (96, 96, 2048),
+    "square": (96, 96, 2048),
+    "smallpt": (64, 64, 2048),
+    "mixedlights": (64, 64, 2048),
+    # many lights: CollectionLighting::distributionInPoint is O(L^2) per hit in the reference, 29 paths/s per
+    # core at L = 1024 -> a coarse frame of the whole view
+    "lightgrid:32x32": (20, 20, 192),
 }
 WORKERS = 8
 
@@ -64,7 +69,7 @@ def make_images():
         q = sum(p[1] for p in parts)
         c = sum(p[2] for p in parts)
         rays = sum(p[3] for p in parts)
-        np.savez_compressed(HERE / f"image_{key.replace('@', '_')}.npz", sum=s.astype(np.float32), sumsq=q.astype(np.float32), count=c.astype(np.uint32),
+        np.savez_compressed(HERE / f"image_{key.replace('@', '_').replace(':', '_')}.npz", sum=s.astype(np.float32), sumsq=q.astype(np.float32), count=c.astype(np.uint32),
                             passes=per * WORKERS, rays=rays, n_rays=16, depth_max=4)
         print(scene, "mean", s.sum() / c.sum(), "rays/path", rays / (W * H * per * WORKERS))
 

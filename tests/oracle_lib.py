@@ -221,6 +221,11 @@ class Oracle(_OutputStage):
         self.lib.ipt_oracle_bvh_build(_p(t, f32p), C.c_uint64(n), nodes.ctypes.data_as(C.c_void_p), _p(ids, u32p), _p(keys, u64p))
         return nodes, ids, keys
 
+    def philox_rounds(self, rounds, c, k):
+        out = (C.c_uint32 * 4)()
+        self.lib.ipt_oracle_philox_rounds(rounds, *[C.c_uint32(v) for v in c], *[C.c_uint32(v) for v in k], out)
+        return list(out)
+
     def philox(self, c, k):
         out = (C.c_uint32 * 4)()
         self.lib.ipt_oracle_philox(*[C.c_uint32(v) for v in c], *[C.c_uint32(v) for v in k], out)

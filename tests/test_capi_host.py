@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/ipt_b200.h but not exported"
     assert declared == set(capi.SIGNATURES), "ctypes binding and header disagree"
-    assert lib.ipt_abi_version() == 2
+    assert lib.ipt_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header(lib):

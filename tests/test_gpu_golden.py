@@ -7,7 +7,7 @@ import pytest
 
 from helpers import SCENES_ANALYTIC, bits
 from ipt_b200 import capi
-from test_oracle_golden import z_scores
+from test_oracle_golden import same_coverage, z_scores
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -137,61 +137,79 @@ def test_mixture_sampling_matches_oracle_distribution(scene, xy, lib, oracle):
     sc.close()
 
 
-@pytest.mark.parametrize("scene,passes", [("box", 512), ("cornell", 512), ("corner", 512), ("openspheres", 512)])
-def test_converged_image_matches_reference(scene, passes, lib):
+def image_stats(s, q, cnt, g, block=8):
+    """The statistical parity procedure of SURVEY.md 8d: per-pixel z = (m_gpu - m_ref) / sqrt(var_gpu/n_gpu + var_ref/n_ref)
+    over the lit pixels, and the relative RMSE of `block` x `block` block means."""
+    H, W = g["sum"].shape
+    z, lit = z_scores(s.astype(np.float64), q.astype(np.float64), cnt, g["sum"].astype(np.float64), g["sumsq"].astype(np.float64), g["count"])
+    mg = s.astype(np.float64) / np.maximum(cnt, 1); mc = g["sum"].astype(np.float64) / np.maximum(g["count"], 1)
+    B = block
+    bg = mg[: H // B * B, : W // B * B].reshape(H // B, B, W // B, B).mean((1, 3)); bc = mc[: H // B * B, : W // B * B].reshape(H // B, B, W // B, B).mean((1, 3))
+    n = int(lit.sum())
+    return dict(n_lit=n, frac3=float((np.abs(z[lit]) < 3).mean()), mean_z=float(z[lit].mean()), std_z=float(z[lit].std()),
+                block_rel_rmse=float(np.sqrt(((bg - bc) ** 2).mean()) / bc.mean()), mean_rel=float((mg.sum() - mc.sum()) / mc.sum()),
+                # the fraction of |z| < 3 of exactly N(0,1) scores is 0.9973 +- sqrt(0.0027 * 0.9973 / n): three standard errors
+                frac3_floor=0.997 - 3.0 * float(np.sqrt(0.0027 * 0.9973 / max(n, 1))))
+
+
+# scene -> device passes. The goldens (tests/golden/image_<scene>.npz, made by make_golden.py) hold sum / sumsq / count of the
+# reference's own estimator (ray_power_recursive 16/8/4/2 with drand48) over 2048 passes; the device renders 8x as many
+# passes with Philox, so the scores are dominated by the golden's own noise.
+IMAGE_SCENES = {"box": 16384, "cornell": 16384, "corner": 16384, "openspheres": 16384, "fractal": 16384, "square": 16384,
+                "smallpt": 16384, "mixedlights": 16384, "lightgrid:32x32": 2048}
+
+
+@pytest.mark.parametrize("scene", list(IMAGE_SCENES))
+def test_converged_image_matches_reference(scene, lib, record_property):
     """BASELINE.json north_star: 'converged images match per pixel within a stated statistical tolerance (mean within
-    3 sigma, image relative RMSE below 1% at high spp)'. Golden = the reference's own estimator with drand48.
-    Tolerances: >= 99% of lit pixels |z| < 3; |mean z| < 0.1; relRMSE of 8x8 block means < 1.5% (the golden itself
-    carries ~1% noise at its 128-256 passes); image mean within 1%."""
-    g = np.load(GOLD / f"image_{scene}.npz")
+    3 sigma, image relative RMSE below 1% at high spp)', with SURVEY.md 8d's tolerances: >= 99.7 % of the lit pixels
+    |z| < 3 (up to the sampling error of that fraction over the frame's pixels), |mean z| < 0.1 (bias detector), relative
+    RMSE of 8x8 block means < 1 %, image mean within 0.5 %. Golden = the UNMODIFIED reference with drand48."""
+    g = np.load(GOLD / f"image_{scene.replace(':', '_')}.npz")
     H, W = g["sum"].shape
     sd = capi.SceneDescription(scene)
     sc = capi.Scene(sd)
-    s, q, cnt, st = sc.render_host(capi.default_params(width=W, height=H, pass_count=passes, seed=2024))
-    assert np.array_equal(cnt > 0, g["count"] > 0)
-    z, lit = z_scores(s.astype(np.float64), q.astype(np.float64), cnt, g["sum"].astype(np.float64), g["sumsq"].astype(np.float64), g["count"])
-    assert (np.abs(z[lit]) < 3).mean() > 0.99, (np.abs(z[lit]) < 3).mean()
-    # bias detector. Per-pixel z is skewed for a heavy-tailed estimator at a few hundred samples (a pixel without its
-    # rare bright path has both a low mean and a low variance estimate), so the sharp statement is on the image total:
-    # difference of the two image sums in units of its standard error.
-    assert abs(z[lit].mean()) < 0.2, z[lit].mean()
-    ng = np.maximum(cnt, 1).astype(np.float64); nc = np.maximum(g["count"], 1).astype(np.float64)
-    var_g = np.maximum(q / ng - (s / ng) ** 2, 0) / ng; var_c = np.maximum(g["sumsq"] / nc - (g["sum"] / nc) ** 2, 0) / nc
-    total_z = ((s / ng).sum() - (g["sum"] / nc).sum()) / np.sqrt(var_g.sum() + var_c.sum())
-    assert abs(total_z) < 4, total_z
-    mg = s / np.maximum(cnt, 1); mc = g["sum"] / np.maximum(g["count"], 1)
-    B = 8
-    bg = mg[: H // B * B, : W // B * B].reshape(H // B, B, W // B, B).mean((1, 3)); bc = mc[: H // B * B, : W // B * B].reshape(H // B, B, W // B, B).mean((1, 3))
-    rel_rmse = np.sqrt(((bg - bc) ** 2).mean()) / bc.mean()
-    assert rel_rmse < 0.015, rel_rmse
-    assert abs(mg.sum() - mc.sum()) / mc.sum() < 0.01
+    s, q, cnt, st = sc.render_host(capi.default_params(width=W, height=H, pass_count=IMAGE_SCENES[scene], seed=2024))
+    assert same_coverage(cnt, IMAGE_SCENES[scene], g["count"], int(g["passes"]))
+    r = image_stats(s, q, cnt, g, block=8 if min(H, W) >= 64 else 4)
+    print(f"IMAGE_STATS {scene} " + " ".join(f"{k}={v:.5g}" for k, v in r.items()))
+    for k, v in r.items():
+        record_property(k, v)
+    assert r["frac3"] >= r["frac3_floor"], r
+    assert abs(r["mean_z"]) < 0.1, r
+    assert r["block_rel_rmse"] < 0.01, r
+    assert abs(r["mean_rel"]) < 0.005, r
     rays_per_path = st.rays / st.paths
     assert rays_per_path < g["rays"] / (W * H * g["passes"]) * 1.001  # pruning only ever removes zero-weight subtrees
     sc.close()
 
 
-@pytest.mark.parametrize("scene", ["box", "cornell"])
-def test_high_spp_image_rmse_below_one_percent(scene, lib):
-    """BASELINE.json north_star: 'image relative RMSE below 1% at high spp'. Golden: the reference's own estimator,
-    64x64, 2048 passes (drand48); device: 16384 passes (Philox). relRMSE of 8x8 block means < 1 %, per-pixel relRMSE
-    bounded by the golden's own noise, >= 99 % of lit pixels within 3 sigma."""
-    g = np.load(GOLD / f"image_{scene}_hi.npz")
-    H, W = g["sum"].shape
+@pytest.mark.parametrize("scene,pos", [("box", (0.0, 0.0, -1.0)), ("box", (-0.7, 0.3, -0.2)), ("mixedlights", (0.2, -0.1, -1.0)), ("mixedlights", (-0.4, 0.5, -0.5)),
+                                       ("lightgrid:3x3", (0.1, -0.3, -1.0)), ("lightgrid:12x12", (0.1, -0.3, -0.5))])
+def test_light_ddf_sampling_matches_reference_distribution(scene, pos, lib, oracle):
+    """Lighting::distributionInPoint(pos)->sample() on the device (DdfFromLight::sample, src/lighting/lighting.cpp:50-59, over
+    Light::sample :93-104 / :172-207, selected by UnionDdf::sample, ddf.cpp:138-154): 40x40-bucket histogram of the device's
+    directions against the histogram of the oracle's (bit-identical to the reference's with drand48) by a two-sample
+    chi-square, failure rates (back-facing samples return the zero vector) within 5 sigma, and every device sample has a
+    positive density under the device's own value()."""
     sd = capi.SceneDescription(scene)
     sc = capi.Scene(sd)
-    s, q, cnt, st = sc.render_host(capi.default_params(width=W, height=H, pass_count=16384, seed=7))
-    mg = s.astype(np.float64) / np.maximum(cnt, 1); mc = g["sum"].astype(np.float64) / np.maximum(g["count"], 1)
-    B = 8
-    bg = mg.reshape(H // B, B, W // B, B).mean((1, 3)); bc = mc.reshape(H // B, B, W // B, B).mean((1, 3))
-    rel_rmse_blocks = np.sqrt(((bg - bc) ** 2).mean()) / bc.mean()
-    assert rel_rmse_blocks < 0.01, rel_rmse_blocks
-    z, lit = z_scores(s.astype(np.float64), q.astype(np.float64), cnt, g["sum"].astype(np.float64), g["sumsq"].astype(np.float64), g["count"])
-    assert (np.abs(z[lit]) < 3).mean() > 0.99
-    assert abs(mg.sum() - mc.sum()) / mc.sum() < 0.005
-    # per-pixel relRMSE is dominated by the CPU golden's noise at 2048 passes; it must not exceed that noise level
-    nc = np.maximum(g["count"], 1).astype(np.float64)
-    sigma_c = np.sqrt(np.maximum(g["sumsq"] / nc - mc * mc, 0) / nc)
-    expected = np.sqrt((sigma_c ** 2).mean()) / mc.mean()
-    per_pixel = np.sqrt(((mg - mc) ** 2).mean()) / mc.mean()
-    assert per_pixel < 1.3 * expected + 0.002, (per_pixel, expected)
+    n = 300000
+    p = np.array(pos, np.float32)
+    w = sc.light_ddf_sample(p, n, seed=4242)
+    ok = np.any(w != 0, axis=1)
+    assert np.allclose(np.linalg.norm(w[ok], axis=1), 1, atol=1e-5)
+    oracle.seed(271828)
+    w_c = oracle.light_ddf_sample(sd.ptr, p, n)
+    hg, rate_g = histogram(w)
+    hc, rate_c = histogram(w_c)
+    assert abs(rate_g - rate_c) < 5 * np.sqrt(0.25 / n) * np.sqrt(2), (rate_g, rate_c)
+    use = (hg + hc) > 20
+    chi2 = ((hg[use] - hc[use]) ** 2 / (hg[use] + hc[use])).sum() / max(use.sum(), 1)
+    assert use.sum() >= 1 and 0.6 < chi2 < 1.4, (chi2, int(use.sum()))
+    # sample() and value() describe the same distribution: sampled directions have positive density
+    v = sc.light_ddf_value(p, w[ok][:20000])
+    assert (v > 0).mean() > 0.999
+    vo = oracle.light_ddf_value(sd.ptr, p, w[ok][:3000])
+    assert np.allclose(v[:3000], vo, rtol=3e-4, atol=1e-6)
     sc.close()

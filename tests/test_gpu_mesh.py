@@ -72,3 +72,30 @@ def test_mesh_render_matches_oracle(lib, oracle):
     assert abs(s8.sum() - o8["sum"].sum()) < 0.05 * o8["sum"].sum() + 1e-6
     assert abs(int(st8.rays) - int(o8["rays"])) < 2e-2 * o8["rays"]
     sc.close()
+
+
+@pytest.mark.parametrize("scene,size,depth,schedule,cpu_passes,gpu_passes", [
+    ("mesh:1000000", 64, 8, [1] * 8, 768, 16384),    # BASELINE configs[2]: depth 8, one child per hit
+    ("mesh:100000", 48, 4, [16, 8, 4, 2], 24, 1024),  # the reference's own tree on a mesh
+])
+def test_mesh_image_z_test_against_oracle(scene, size, depth, schedule, cpu_passes, gpu_passes, lib, oracle):
+    """Converged-image parity of the mesh path (the reference has no mesh geometry, SURVEY S1: the oracle's GeometryMesh over
+    the CPU LBVH is the checker). INDEPENDENT random numbers on the two sides (different Philox keys): per-pixel z-test of
+    the means, bias detector, block relRMSE — SURVEY 8d's procedure, same assertions as test_converged_image_matches_reference."""
+    from test_gpu_golden import image_stats
+
+    sd = capi.SceneDescription(scene)
+    sc = capi.Scene(sd)
+    kw = dict(width=size, height=size, depth_max=depth, schedule=schedule)
+    o = oracle.render(sd.ptr, capi.default_params(pass_count=cpu_passes, seed=1234, **kw), oracle_lib.RNG_PHILOX, 1)
+    s, q, cnt, st = sc.render_host(capi.default_params(pass_count=gpu_passes, seed=98765, **kw))
+    g = dict(sum=o["sum"], sumsq=o["sumsq"], count=o["counters"])
+    assert np.array_equal(cnt > 0, g["count"] > 0)
+    r = image_stats(s, q, cnt, g)
+    print(f"IMAGE_STATS {scene} depth {depth} " + " ".join(f"{k}={v:.5g}" for k, v in r.items()))
+    assert r["frac3"] >= r["frac3_floor"], r
+    assert abs(r["mean_z"]) < 0.1, r
+    assert r["block_rel_rmse"] < 0.01, r
+    assert abs(r["mean_rel"]) < 0.005, r
+    assert abs(st.rays / st.paths - o["rays"] / o["counters"].sum()) < 0.01 * st.rays / st.paths
+    sc.close()

@@ -122,8 +122,13 @@ def test_progressive_session_keys_checkpoint_and_resume(lib, oracle, tmp_path):
     got = np.array([list(a.camera.position), list(a.camera.direction), list(a.camera.right), list(a.camera.up)], np.float32)
     assert np.array_equal(bits(got), bits(want))
     a.step(1)
-    ck = tmp_path / "session.npz"
-    a.checkpoint(ck)
+    ck = tmp_path / "session"          # no suffix: the file written and the file looked for must be the same one
+    written = a.checkpoint(ck)
+    assert written == tmp_path / "session.npz" and written.exists() and not list(tmp_path.glob("*.tmp*"))
+    with pytest.raises(ValueError):     # another estimator must not resume these accumulators
+        ProgressiveSession(checkpoint_path=ck, **dict(kw, depth_max=3))
+    with pytest.raises(ValueError):
+        ProgressiveSession(checkpoint_path=ck, **dict(kw, scene_name="corner"))
     a.step(2)
     s_a, q_a, c_a = a.plane.download()
     assert a.samples_per_pixel == 6 and (c_a.sum() == 6 * 64 * 64) and not np.allclose(s_a / 6, before / 4, atol=1e-3)  # another view

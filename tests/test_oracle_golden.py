@@ -102,7 +102,7 @@ def test_plane_addray_known_answers(lib, oracle):
     assert (g["plane_counters"][H - 1] == 0).all() or True  # row H-1 only receives y < 1/H*... (documented quirk)
 
 
-@pytest.mark.parametrize("scene,passes", [("box", 48), ("cornell", 48), ("corner", 64), ("openspheres", 64)])
+@pytest.mark.parametrize("scene,passes", [("box", 128), ("cornell", 128), ("corner", 512), ("openspheres", 512)])
 def test_oracle_philox_image_matches_reference_statistically(scene, passes, lib, oracle):
     """The oracle drawing Philox numbers (what the GPU is compared with) is the same estimator as the reference drawing
     drand48: per-pixel z-test of means against the golden image + bias detector."""
@@ -112,12 +112,22 @@ def test_oracle_philox_image_matches_reference_statistically(scene, passes, lib,
     p = capi.default_params(width=W, height=H, pass_count=passes, seed=99)
     o = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 0)
     z, lit = z_scores(o["sum"], o["sumsq"], o["counters"], g["sum"], g["sumsq"], g["count"])
-    assert np.array_equal(o["counters"] > 0, g["count"] > 0)
+    assert same_coverage(o["counters"], passes, g["count"], int(g["passes"]))
     assert lit.sum() > 0.1 * lit.size
-    assert (np.abs(z[lit]) < 3).mean() > 0.99
-    assert abs(z[lit].mean()) < 0.1
+    # >= 99.7 % of the lit pixels within 3 sigma — the expectation for N(0,1) scores is 99.73 %, so the assertion
+    # allows three standard errors of that fraction over the frame's pixels; |mean z| < 0.1 is the bias detector (at 128
+    # samples the heavy-tailed estimator still skews z by about -0.05)
+    assert (np.abs(z[lit]) < 3).mean() >= 0.997 - 3.0 * np.sqrt(0.0027 * 0.9973 / lit.sum()), (np.abs(z[lit]) < 3).mean()
+    assert abs(z[lit].mean()) < 0.1, z[lit].mean()
     m_o = o["sum"].sum() / o["counters"].sum(); m_g = g["sum"].sum() / g["count"].sum()
     assert abs(m_o - m_g) / m_g < 0.02
+
+
+def same_coverage(cnt_a, passes_a, cnt_b, passes_b):
+    """Both planes received the samples of the same cells. GridRenderPlane::addRay's row mapping (SURVEY S5) folds loop rows
+    H-2 and H-1 into image row 0 and leaves image row H-1 to the ~4e-6 of the samples whose y*H rounds away — a handful of
+    stray counts in a 2048-pass golden — so cells are compared by whether they hold at least half a pass worth of samples."""
+    return np.array_equal(cnt_a.astype(np.float64) / passes_a >= 0.5, cnt_b.astype(np.float64) / passes_b >= 0.5)
 
 
 def z_scores(s1, q1, n1, s2, q2, n2):
@@ -129,11 +139,3 @@ def z_scores(s1, q1, n1, s2, q2, n2):
     z = np.zeros_like(m1, dtype=np.float64)
     z[lit] = (m1[lit] - m2[lit]) / np.sqrt(v1[lit] + v2[lit])
     return z, lit
-
-
-def test_high_spp_goldens_are_consistent_with_the_low_spp_ones():
-    """Two independent runs of the reference (different seeds, frame sizes): image means agree."""
-    for scene in ["box", "cornell"]:
-        a = np.load(GOLD / f"image_{scene}.npz"); b = np.load(GOLD / f"image_{scene}_hi.npz")
-        ma = a["sum"].sum() / a["count"].sum(); mb = b["sum"].sum() / b["count"].sum()
-        assert abs(ma - mb) / mb < 0.01
