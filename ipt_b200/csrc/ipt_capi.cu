@@ -457,6 +457,9 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
             mats[i].ws = m.ks / (m.kd + m.ks);
         }
         mats[i].exponent = m.exponent;
+        const float n_lobe = m.ddf == IPT_DDF_GLOSSY ? (float)(int)m.exponent : 1.0f;
+        mats[i].inv_np1 = 1.0f / (n_lobe + 1.0f);
+        mats[i].lobe_norm = (n_lobe + 1.0f) * (0.5f / IPT_PI_F);
     }
 
     CUDA_TRY(cudaSetDevice(device));

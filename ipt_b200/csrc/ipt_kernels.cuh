@@ -82,7 +82,7 @@ __device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2])
 // the incoming direction, which only the glossy lobe (reflect(d, n)) needs. The parent ray record cannot be re-read
 // at shading time: the shade kernel is already overwriting the ray queue with the next depth.
 __device__ __forceinline__ float2 oct_encode(f3 d) {
-    float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(fabsf(d.x), fabsf(d.y)), fabsf(d.z)));
+    float inv = frcp(__fadd_rn(__fadd_rn(fabsf(d.x), fabsf(d.y)), fabsf(d.z))); // 1 ulp: the decoder re-normalises
     float px = pmul(d.x, inv), py = pmul(d.y, inv);
     if (d.z < 0.0f) {
         float tx = copysignf(__fsub_rn(1.0f, fabsf(py)), px);
@@ -187,7 +187,7 @@ __device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, f
 //               needs: its own traceRayToLight and the density of the mixture it was sampled from
 // An LBVH is at most 63 key bits + 32 tie-breaking index bits deep, and the walk pushes one sibling per level.
 #define IPT_LBVH_MAX_HEIGHT 96
-template <int MODE>
+template <int MODE, bool X>
 __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& best_len, TraceCounters& tc) {
     constexpr bool NEAREST = MODE != LQ_PDF, PDF = MODE != LQ_NEAREST;
     float pdf_sum = 0.0f;
@@ -205,12 +205,12 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
             f8 r1 = ldg256(&S.light_recs[4 * (size_t)pos + 2]);
             ++tc.lights;
             f3 corner = mk3(r0.v[0], r0.v[1], r0.v[2]), n = mk3(r0.v[3], r0.v[4], r0.v[5]), rel;
-            float t = isect_parallelogram(corner, n, mk3(r0.v[6], r0.v[7], r1.v[0]), mk3(r1.v[1], r1.v[2], r1.v[3]), r1.v[5] != 0.0f, o, d, &rel);
+            float t = isect_parallelogram<X>(corner, n, mk3(r0.v[6], r0.v[7], r1.v[0]), mk3(r1.v[1], r1.v[2], r1.v[3]), r1.v[5] != 0.0f, o, d, &rel);
             if (t != IPT_INF) {
                 f3 hp = xadd3(corner, rel);
                 uint32_t orig = __float_as_uint(r1.v[4]);
                 if (NEAREST) {
-                    float len = xlength3(xsub3(hp, o));
+                    float len = X ? xlength3(xsub3(hp, o)) : t; // unit direction: see trace_one_light
                     if (len < best_len || (len == best_len && orig < which)) { best_len = len; which = orig; lpos = hp; }
                 }
                 if (PDF) {
@@ -276,8 +276,8 @@ __device__ __forceinline__ bool trace_lights(const DevScene& S, f3 o, f3 d, uint
     ldist = 0.0f;
     lpdf = 0.0f;
     if (has_light_bvh<SPEC>(S)) {
-        if (PDF) lpdf = light_bvh_query<LQ_BOTH>(S, o, d, which, lpos, ldist, tc);
-        else light_bvh_query<LQ_NEAREST>(S, o, d, which, lpos, ldist, tc);
+        if (PDF) lpdf = light_bvh_query<LQ_BOTH, X>(S, o, d, which, lpos, ldist, tc);
+        else light_bvh_query<LQ_NEAREST, X>(S, o, d, which, lpos, ldist, tc);
         return which != IPT_NO_HIT;
     }
     if (SPEC == SPEC_LIGHT_BVH) return false; // unreachable: the LBVH branch above always returns
@@ -473,7 +473,8 @@ __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCt
 }
 
 // First node visit of the light LBVH: false = the ray misses both root boxes, i.e. there is no light along it.
-__device__ __forceinline__ bool light_root_hit(const DevScene& S, f3 o, f3 d) {
+__device__ __forceinline__ bool light_root_hit(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
+    ++tc.light_nodes;
     f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     f8 n0 = ldg256(&S.light_nodes[0]);
     f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[0]) + 32);
@@ -502,7 +503,9 @@ struct ExtendCounters {
 // The body of k_extend<.., LAST = false> for one parked child ray of depth `depth` (entry k of the warp's queue; all 32
 // lanes call this, `valid` masks the drain): trace_scene, weight resolution, emission, and the warp-aggregated append
 // of the surface hits to the hit set of `depth`.
-template <bool SMALLPT, int SPEC, bool X>
+// LIGHTS = false: the caller has established that no light lies along the ray (it misses the root boxes of the light LBVH),
+// so only Geometry::traceRay runs; the light part of the mixture density is 0 and the ray cannot end on a light.
+template <bool SMALLPT, int SPEC, bool X, bool LIGHTS = true>
 __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx& C, const float* dq, uint32_t k, bool valid, uint32_t depth,
                                               TraceCounters& tc, ExtendCounters& ec) {
     const uint32_t lane = threadIdx.x & 31;
@@ -515,7 +518,13 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
         o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
         d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
         ctag = __float_as_uint(dq[8 * IPT_PARK + k]);
-        oc = trace_scene<SMALLPT, false, SPEC, X>(S, o, d, tc);
+        if (LIGHTS) oc = trace_scene<SMALLPT, false, SPEC, X>(S, o, d, tc);
+        else {
+            oc.surf = trace_geometry<SMALLPT, false, IPT_SPEC_FAST_GEOMETRY(SPEC), X>(S, o, d, tc);
+            oc.kind = oc.surf.prim != IPT_NO_HIT ? 1u : 0u;
+            oc.light = IPT_NO_HIT;
+            oc.light_pdf = 0.0f;
+        }
         wr = resolve_weight(S, dq[6 * IPT_PARK + k], dq[7 * IPT_PARK + k], oc.light_pdf);
         if (!isfinite(wr)) ++ec.dropped; // non-finite multiplier (main.cpp:175): drop this sample
         else if (oc.kind == 2) {
@@ -559,6 +568,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_children = C.schedule[depth];
     const float inv_n = 1.0f / (float)n_children;
+    const bool keep_zero = (C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT) != 0;
     uint32_t n_failed = 0, n_pruned = 0, n_dropped = 0;
     uint32_t n_fused = 0, n_light = 0, n_surface = 0;
     ExtendCounters ec{0, 0, 0, 0};
@@ -567,9 +577,14 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
     // same k_extend<.., X = false> uses for queued rays of depth > 0
     constexpr bool X = !IPT_FAST_SECONDARY;
     constexpr int PARK_WORDS = 9;
-    __shared__ float dq_all[FUSE != FUSE_NONE ? (256 / 32) * PARK_WORDS * IPT_PARK : 1];
-    float* dq = dq_all + (FUSE != FUSE_NONE ? (threadIdx.x >> 5) * PARK_WORDS * IPT_PARK : 0); // this warp's parked rays
-    uint32_t qn = 0;                                                            // warp-uniform
+    // many-light scenes, non-last depths: children are regrouped by whether they can see a light at all (the root boxes of
+    // the light LBVH): the ones that can walk the LBVH 32 at a time, the others only intersect the geometry
+    constexpr bool TWO_Q = FUSE == FUSE_NEXT && SPEC == SPEC_LIGHT_BVH;
+    constexpr int QUEUES = TWO_Q ? 2 : 1;
+    __shared__ float dq_all[FUSE != FUSE_NONE ? (256 / 32) * PARK_WORDS * IPT_PARK * QUEUES : 1];
+    float* dq = dq_all + (FUSE != FUSE_NONE ? (threadIdx.x >> 5) * PARK_WORDS * IPT_PARK * QUEUES : 0); // this warp's parked rays
+    float* dq2 = dq + (TWO_Q ? PARK_WORDS * IPT_PARK : 0);
+    uint32_t qn = 0, qn2 = 0;                                                   // warp-uniform
     uint32_t* out_count = &C.cnt[2 * (depth + 1)];
     for (uint32_t base = gwarp * 32; base < n; base += warps * 32) {
         uint32_t i = base + lane;
@@ -597,7 +612,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             const float4* mp = reinterpret_cast<const float4*>(&S.mats_g[material]);
             float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
             DevMaterial m;
-            m.ddf = __float_as_uint(m0.x); m.albedo = m0.y; m.wd = m0.z; m.ws = m0.w; m.exponent = m1.x;
+            m.ddf = __float_as_uint(m0.x); m.albedo = m0.y; m.wd = m0.z; m.ws = m0.w; m.exponent = m1.x; m.inv_np1 = m1.y; m.lobe_norm = m1.z;
             albedo = m.albedo;
             f3 din = mk3(0, 0, 0);
             if (SPEC != SPEC_LAMBERT_BOX && m.ddf == IPT_DDF_GLOSSY) din = oct_decode(__uint_as_float(b.z), __uint_as_float(b.w)); // only the glossy lobe needs it
@@ -605,6 +620,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             bn = make_basis(normal);
             bl = (SPEC != SPEC_LAMBERT_BOX && m.ddf == IPT_DDF_GLOSSY) ? make_basis(sdf.refl) : bn;
         }
+        const float hit_k = pmul(pmul(thr, albedo), inv_n);
         for (uint32_t c = 0; c < n_children; ++c) {
             bool emit = false;
             f3 w = mk3(0, 0, 0);
@@ -622,20 +638,26 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     float sv = sdf_value<SPEC == SPEC_LAMBERT_BOX>(sdf, w);
                     // the ray's own light intersection (k_extend, or the fused block below) also yields the light part of
                     // the mixture density, so the weight K*sv/mix is resolved there; sv == 0 already means weight 0
-                    wgt = pmul(pmul(thr, albedo), inv_n);
+                    wgt = hit_k; // throughput * albedo / n of this hit
                     child_sv = sv;
-                    if (!isfinite(sv) || !isfinite(wgt)) ++n_dropped;
-                    else if ((sv == 0.0f || wgt == 0.0f) && !(C.flags & IPT_FLAG_KEEP_ZERO_WEIGHT)) ++n_pruned;
+                    // sv and wgt are >= 0 or non-finite: their sum is finite iff both are, their minimum is 0 iff one is
+                    if (!(__fadd_rn(sv, wgt) < IPT_INF)) ++n_dropped;
+                    else if (fminf(sv, wgt) == 0.0f && !keep_zero) ++n_pruned;
                     else emit = true;
                 }
             }
             if (FUSE == FUSE_NEXT) {
-                uint32_t pb = __ballot_sync(0xffffffffu, emit);
+                if (emit) ++n_fused;
+                const uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
+                bool to_lights = emit, plain = false;
+                if (TWO_Q) {
+                    to_lights = emit && light_root_hit(S, pos, w, tc);
+                    plain = emit && !to_lights;
+                }
+                uint32_t pb = __ballot_sync(0xffffffffu, to_lights);
                 if (pb) {
-                    if (emit) {
-                        ++n_fused;
+                    if (to_lights) {
                         uint32_t k = qn + __popc(pb & ((1u << lane) - 1u));
-                        uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
                         dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
                         dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
                         dq[6 * IPT_PARK + k] = wgt; dq[7 * IPT_PARK + k] = child_sv; dq[8 * IPT_PARK + k] = __uint_as_float(ctag);
@@ -646,6 +668,24 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                         qn -= 32;
                         extend_parked<SMALLPT, SPEC, X>(S, C, dq, qn + lane, true, depth + 1, tc, ec);
                         __syncwarp();
+                    }
+                }
+                if (TWO_Q) {
+                    uint32_t pb2 = __ballot_sync(0xffffffffu, plain);
+                    if (pb2) {
+                        if (plain) {
+                            uint32_t k = qn2 + __popc(pb2 & ((1u << lane) - 1u));
+                            dq2[0 * IPT_PARK + k] = pos.x; dq2[1 * IPT_PARK + k] = pos.y; dq2[2 * IPT_PARK + k] = pos.z;
+                            dq2[3 * IPT_PARK + k] = w.x; dq2[4 * IPT_PARK + k] = w.y; dq2[5 * IPT_PARK + k] = w.z;
+                            dq2[6 * IPT_PARK + k] = wgt; dq2[7 * IPT_PARK + k] = child_sv; dq2[8 * IPT_PARK + k] = __uint_as_float(ctag);
+                        }
+                        qn2 += __popc(pb2);
+                        __syncwarp();
+                        if (qn2 >= 32) {
+                            qn2 -= 32;
+                            extend_parked<SMALLPT, SPEC, X, false>(S, C, dq2, qn2 + lane, true, depth + 1, tc, ec);
+                            __syncwarp();
+                        }
                     }
                 }
                 continue;
@@ -660,7 +700,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     bool parkb = false;
                     if (emit) {
                         ++n_fused;
-                        parkb = light_root_hit(S, pos, w);
+                        parkb = light_root_hit(S, pos, w, tc);
                     }
                     uint32_t pbb = __ballot_sync(0xffffffffu, parkb);
                     if (pbb) {
@@ -735,6 +775,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
         else resolve_parked<SMALLPT, SPEC, X>(S, C, dq, lane, tc, n_light, n_surface);
     }
     if (FUSE == FUSE_NEXT && qn) extend_parked<SMALLPT, SPEC, X>(S, C, dq, lane, lane < qn, depth + 1, tc, ec); // drain (warp-uniform qn)
+    if (TWO_Q && qn2) extend_parked<SMALLPT, SPEC, X, false>(S, C, dq2, lane, lane < qn2, depth + 1, tc, ec);
     n_light += ec.light; n_surface += ec.surface; n_dropped += ec.dropped;
     flush_stat(C.stats, ST_FAILED, n_failed);
     flush_stat(C.stats, ST_PRUNED, n_pruned);

@@ -113,8 +113,8 @@ __device__ __forceinline__ Sdf make_sdf(const DevMaterial& m, f3 normal, f3 dir_
     s.wd = glossy ? m.wd : 1.0f;
     s.ws = glossy ? m.ws : 0.0f;
     s.exponent = glossy ? (float)(int)m.exponent : 1.0f;
-    s.inv_np1 = 1.0f / (s.exponent + 1.0f);
-    s.lobe_norm = (s.exponent + 1.0f) * (0.5f / IPT_PI_F);
+    s.inv_np1 = m.inv_np1;
+    s.lobe_norm = m.lobe_norm;
     s.refl = glossy ? reflect3(dir_in, normal) : normal;
     return s;
 }
@@ -211,7 +211,7 @@ __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float 
     return dir;
 }
 
-template <int MODE>
+template <int MODE, bool X>
 __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, uint32_t& which, f3& lpos, float& best_len, TraceCounters& tc); // ipt_kernels.cuh
 
 // UnionDdf::value over [lights..., sdf] (src/libddf/ddf.cpp:156-162) with the weights of main.cpp:143
@@ -226,7 +226,7 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
         f3 lpos;
         float best_len;
         TraceCounters tc{0, 0, 0, 0};
-        lp = light_bvh_query<0 /* LQ_PDF */>(S, pos, w, which, lpos, best_len, tc);
+        lp = light_bvh_query<0 /* LQ_PDF */, true>(S, pos, w, which, lpos, best_len, tc);
     } else {
         for (uint32_t i = 0; i < S.n_lights; ++i) {
             const DevLight& L = S.lights_g[i];

@@ -33,13 +33,14 @@ IMAGE_JOBS = {  # scene: (W, H, passes). 2048 passes: SURVEY 8d's tolerances (99
     "cornell": (96, 96, 2048),
     "corner": (96, 96, 2048),
     "openspheres": (96, 96, 2048),
-    "fractal": (96, 96, 2048),
-    "square": (96, 96, 2048),
+    # cheap scenes with rare bright paths: many more passes, so that the golden's own per-pixel variance estimates are sound
+    "fractal": (96, 96, 65536),
+    "square": (96, 96, 32768),
     "smallpt": (64, 64, 2048),
     "mixedlights": (64, 64, 2048),
     # many lights: CollectionLighting::distributionInPoint is O(L^2) per hit in the reference, 29 paths/s per
     # core at L = 1024 -> a coarse frame of the whole view
-    "lightgrid:32x32": (20, 20, 192),
+    "lightgrid:32x32": (20, 20, 768),
 }
 WORKERS = 8
 

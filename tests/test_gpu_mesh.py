@@ -76,7 +76,7 @@ def test_mesh_render_matches_oracle(lib, oracle):
 
 @pytest.mark.parametrize("scene,size,depth,schedule,cpu_passes,gpu_passes", [
     ("mesh:1000000", 64, 8, [1] * 8, 768, 16384),    # BASELINE configs[2]: depth 8, one child per hit
-    ("mesh:100000", 48, 4, [16, 8, 4, 2], 24, 1024),  # the reference's own tree on a mesh
+    ("mesh:100000", 32, 4, [16, 8, 4, 2], 192, 4096),  # the reference's own tree on a mesh
 ])
 def test_mesh_image_z_test_against_oracle(scene, size, depth, schedule, cpu_passes, gpu_passes, lib, oracle):
     """Converged-image parity of the mesh path (the reference has no mesh geometry, SURVEY S1: the oracle's GeometryMesh over
@@ -90,8 +90,10 @@ def test_mesh_image_z_test_against_oracle(scene, size, depth, schedule, cpu_pass
     o = oracle.render(sd.ptr, capi.default_params(pass_count=cpu_passes, seed=1234, **kw), oracle_lib.RNG_PHILOX, 1)
     s, q, cnt, st = sc.render_host(capi.default_params(pass_count=gpu_passes, seed=98765, **kw))
     g = dict(sum=o["sum"], sumsq=o["sumsq"], count=o["counters"])
-    assert np.array_equal(cnt > 0, g["count"] > 0)
-    r = image_stats(s, q, cnt, g)
+    from test_oracle_golden import same_coverage
+
+    assert same_coverage(cnt, gpu_passes, g["count"], cpu_passes)
+    r = image_stats(s, q, cnt, g, block=8 if size >= 64 else 4)
     print(f"IMAGE_STATS {scene} depth {depth} " + " ".join(f"{k}={v:.5g}" for k, v in r.items()))
     assert r["frac3"] >= r["frac3_floor"], r
     assert abs(r["mean_z"]) < 0.1, r

@@ -32,7 +32,8 @@ for name in sel:
     out = dict(config=name, scene=c["scene"], frame=[c["width"], c["height"]], tile=c.get("tile"), schedule=c["schedule"], passes=c["passes"],
                mpaths_per_s=st.paths / st.ms_total / 1e3, mrays_per_s=st.rays / st.ms_total / 1e3, rays_per_path=st.rays / st.paths,
                ms_total=st.ms_total, ms_extend=st.ms_extend, ms_shade=st.ms_shade, bvh_nodes_per_ray=st.bvh_nodes_visited / max(st.rays, 1),
-               tris_per_ray=st.triangles_tested / max(st.rays, 1), image_mean=float(s.sum() / max(cnt.sum(), 1)),
+               tris_per_ray=st.triangles_tested / max(st.rays, 1),
+               light_nodes_per_ray=st.light_bvh_nodes_visited / max(st.rays, 1), lights_per_ray=st.lights_tested / max(st.rays, 1), image_mean=float(s.sum() / max(cnt.sum(), 1)),
                scene_desc_s=t1 - t0, scene_create_s=t2 - t1, launches=st.kernel_launches)
     print(json.dumps(out), flush=True)
     pl.close(); sc.close()
