@@ -281,6 +281,11 @@ int ipt_plane_device_ptrs(ipt_plane* plane, float** d_sum, float** d_sumsq, uint
  * One grouped launch (ncclGroupStart/End): the two float arrays as one message when they are contiguous (they are in a
  * plane made by ipt_plane_create: one packed block sum | sumsq | count), then the counters. */
 int ipt_plane_allreduce(ipt_plane* plane, void* nccl_comm, float* ms /* device time of the collective, may be NULL */);
+/* dst += src, element-wise over sum / sumsq / count. The two planes may belong to scenes on DIFFERENT devices of this
+ * process (src is fetched with a peer copy over NVLink, or staged by the driver where peer access is unavailable): how a
+ * single-process, one-thread-per-GPU host (the shape of the reference's own driver, src/main.cpp:258-277) merges its
+ * per-GPU pass ranges without NCCL. Same frame size required; src is left unchanged. */
+int ipt_plane_merge(ipt_plane* dst, ipt_plane* src);
 /* GridRenderPlane state after the same samples: pixels = sum/count, pixel_counters, max_value (GridRenderPlane.h:9-12). */
 int ipt_plane_resolve(ipt_plane* plane, float* pixels, uint64_t* pixel_counters, float* max_value);
 

@@ -118,6 +118,7 @@ SIGNATURES = {
     "ipt_plane_upload": (C.c_int, [_vp, f32p, f32p, u32p]),
     "ipt_plane_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "ipt_plane_allreduce": (C.c_int, [_vp, _vp, f32p]),
+    "ipt_plane_merge": (C.c_int, [_vp, _vp]),
     "ipt_plane_resolve": (C.c_int, [_vp, f32p, u64p, f32p]),
     "ipt_image_glare": (C.c_int, [C.c_int, f32p, C.c_uint32, C.c_uint32, C.c_float, f32p, u32p]),
     "ipt_image_normalize": (C.c_int, [C.c_int, f32p, C.c_uint32, C.c_uint32, f32p]),
@@ -392,6 +393,10 @@ class Plane:
         ms = C.c_float(0)
         check(load().ipt_plane_allreduce(self.handle, nccl_comm, C.byref(ms)))
         return ms.value
+
+    def merge(self, other: "Plane"):
+        """ipt_plane_merge: self += other (the planes may live on different devices of this process)."""
+        check(load().ipt_plane_merge(self.handle, other.handle))
 
     def download_into(self, s, q, c):
         """ipt_plane_download into caller-owned (e.g. pinned) host arrays."""

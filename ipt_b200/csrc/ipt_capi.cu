@@ -251,6 +251,16 @@ __global__ void k_plane_add_rays(RenderCtx C, size_t n, const float* __restrict_
     atomicAdd(&C.count[cell], 1u);
 }
 
+__global__ void k_plane_merge(float* __restrict__ sum, float* __restrict__ sumsq, uint32_t* __restrict__ count, const float* __restrict__ s2,
+                              const float* __restrict__ q2, const uint32_t* __restrict__ c2, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        sum[i] += s2[i];
+        sumsq[i] += q2[i];
+        count[i] += c2[i];
+    }
+}
+
 __global__ void k_plane_resolve(const float* __restrict__ sum, const uint32_t* __restrict__ count, size_t n, float* pixels) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pixels[i] = count[i] ? sum[i] / (float)count[i] : 0.0f;
@@ -958,6 +968,37 @@ int ipt_plane_allreduce(ipt_plane* p, void* nccl_comm, float* ms) {
     CUDA_TRY(cudaEventRecord(p->scene->ev_end, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (ms) CUDA_TRY(cudaEventElapsedTime(ms, p->scene->ev_begin, p->scene->ev_end));
+    return IPT_OK;
+}
+int ipt_plane_merge(ipt_plane* dst, ipt_plane* src) {
+    if (!dst || !src) return fail(IPT_ERR_INVALID, "null plane");
+    if (dst == src) return fail(IPT_ERR_INVALID, "a plane cannot be merged into itself");
+    if (dst->width != src->width || dst->height != src->height) return fail(IPT_ERR_INVALID, "planes of different frame sizes");
+    // both scenes are locked (in address order: two threads merging in opposite directions cannot deadlock)
+    ipt_scene* a = dst->scene < src->scene ? dst->scene : src->scene;
+    ipt_scene* b = dst->scene < src->scene ? src->scene : dst->scene;
+    std::lock_guard<std::recursive_mutex> lock_a(a->mu);
+    std::lock_guard<std::recursive_mutex> lock_b(b->mu);
+    const size_t n = (size_t)dst->width * dst->height;
+    const int ddev = dst->scene->device, sdev = src->scene->device;
+    CUDA_TRY(cudaSetDevice(sdev));
+    CUDA_TRY(cudaStreamSynchronize(src->scene->stream)); // src's last render / merge has landed
+    CUDA_TRY(cudaSetDevice(ddev));
+    cudaStream_t st = dst->scene->stream;
+    const float *s2 = src->sum, *q2 = src->sumsq;
+    const uint32_t* c2 = src->count;
+    DevBuf<float> staged;
+    if (ddev != sdev) {
+        CUDA_TRY(staged.alloc(3 * n));
+        CUDA_TRY(cudaMemcpyPeerAsync(staged.p, ddev, src->sum, sdev, 4 * n, st));
+        CUDA_TRY(cudaMemcpyPeerAsync(staged.p + n, ddev, src->sumsq, sdev, 4 * n, st));
+        CUDA_TRY(cudaMemcpyPeerAsync(staged.p + 2 * n, ddev, src->count, sdev, 4 * n, st));
+        s2 = staged.p; q2 = staged.p + n; c2 = reinterpret_cast<const uint32_t*>(staged.p + 2 * n);
+    }
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)dst->scene->sm_count * 8);
+    k_plane_merge<<<blocks, 256, 0, st>>>(dst->sum, dst->sumsq, dst->count, s2, q2, c2, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
     return IPT_OK;
 }
 int ipt_plane_resolve(ipt_plane* p, float* pixels, uint64_t* pixel_counters, float* max_value) {

@@ -3,11 +3,29 @@
 
 #include "glm_order.hpp"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <tuple>
+
+// Built against the reference's own sources (its src/ directory on the include path), the reference's concrete classes
+// that expose what the device needs are accepted as Scene members and as the render plane (see render_sample).
+#if defined(__has_include)
+#if __has_include(<SimpleCamera.h>) && __has_include(<GridRenderPlane.h>) && __has_include(<geometry/GeometrySphereInBox.h>)
+#define IPT_B200_REFERENCE_CLASSES 1
+#include <GridRenderPlane.h>
+#include <SimpleCamera.h>
+#include <geometry/FractalSpheres.h>
+#include <geometry/GeometryCorner.h>
+#include <geometry/GeometryFloor.h>
+#include <geometry/GeometryOpenSpheres.h>
+#include <geometry/GeometrySmallPt.h>
+#include <geometry/GeometrySphereInBox.h>
+#endif
+#endif
 
 namespace ipt_b200 {
 
@@ -117,6 +135,7 @@ private:
 uint32_t DeviceGeometry::addMaterial(const ipt_material& m) {
     data_.materials.push_back(m);
     ctx_.reset();
+    ++revision_;
     return (uint32_t)data_.materials.size() - 1;
 }
 void DeviceGeometry::addBoxPlane(glm::vec3 plane, uint32_t material) {
@@ -126,6 +145,7 @@ void DeviceGeometry::addBoxPlane(glm::vec3 plane, uint32_t material) {
     put(p.p, plane);
     data_.prims.push_back(p);
     ctx_.reset();
+    ++revision_;
 }
 void DeviceGeometry::addSphere(glm::vec3 centre, float radius, float curvature, uint32_t material) {
     ipt_prim p{};
@@ -136,6 +156,7 @@ void DeviceGeometry::addSphere(glm::vec3 centre, float radius, float curvature, 
     p.curvature = curvature;
     data_.prims.push_back(p);
     ctx_.reset();
+    ++revision_;
 }
 void DeviceGeometry::addSmallPtSphere(glm::vec3 centre, float radius, uint32_t material) {
     ipt_prim p{};
@@ -147,11 +168,13 @@ void DeviceGeometry::addSmallPtSphere(glm::vec3 centre, float radius, uint32_t m
     p.curvature = (float)(-1.0 / (double)radius);
     data_.prims.push_back(p);
     ctx_.reset();
+    ++revision_;
 }
 void DeviceGeometry::setTriangles(const float* t, size_t count, uint32_t material) {
     data_.triangles.assign(t, t + 9 * count);
     data_.triangle_material = material;
     ctx_.reset();
+    ++revision_;
 }
 std::shared_ptr<DeviceGeometry> DeviceGeometry::fromSampleScene(const char* name) {
     ipt_scene_desc* d = nullptr;
@@ -395,54 +418,189 @@ Scene make_scene(const char* name) {
 
 // ---- the hot path ---------------------------------------------------------------------------------------------
 namespace {
+// Device replicas of the scenes seen so far, keyed by the identity of the three Scene members and the device. The entry
+// keeps weak references: when a member has been destroyed (and its address possibly reused by another object) the entry
+// is stale and is rebuilt.
+struct CachedContext {
+    std::weak_ptr<const Geometry> geometry;
+    std::weak_ptr<const Lighting> lighting;
+    std::weak_ptr<const Camera> camera;
+    std::shared_ptr<DeviceContext> ctx;
+    uint64_t geometry_revision = 0, lighting_revision = 0;
+    bool alive() const { return !geometry.expired() && !lighting.expired() && !camera.expired(); }
+};
 std::mutex g_cache_mu;
-std::map<std::tuple<const void*, const void*, const void*, int>, std::shared_ptr<DeviceContext>> g_cache;
+std::map<std::tuple<const void*, const void*, const void*, int>, CachedContext> g_cache;
+
+#ifdef IPT_B200_REFERENCE_CLASSES
+// The reference's data-free geometries: the class IS the scene (its primitives are literals inside traceRay).
+const char* reference_geometry_name(const Geometry* g) {
+    if (dynamic_cast<const GeometrySphereInBox*>(g)) return "box";       // GeometrySphereInBox.cpp:11-17
+    if (dynamic_cast<const GeometryFloor*>(g)) return "square";          // GeometryFloor.cpp:10-23
+    if (dynamic_cast<const GeometryCorner*>(g)) return "corner";         // GeometryCorner.cpp:10-39
+    if (dynamic_cast<const GeometryOpenSpheres*>(g)) return "openspheres"; // GeometryOpenSpheres.cpp:12-68
+    if (dynamic_cast<const FractalSpheres*>(g)) return "fractal";        // FractalSpheres.cpp:16-97
+    if (dynamic_cast<const GeometrySmallPt*>(g)) return "smallpt";       // GeometrySmallPt.cpp:12-61
+    return nullptr;
+}
+#endif
+
+bool export_geometry(const Geometry* g, SceneBuilder& b) {
+    if (const DeviceExportable* e = dynamic_cast<const DeviceExportable*>(g)) { e->exportTo(b); return true; }
+#ifdef IPT_B200_REFERENCE_CLASSES
+    if (const char* name = reference_geometry_name(g)) { DeviceGeometry::fromSampleScene(name)->exportTo(b); return true; }
+#endif
+    return false;
+}
+bool export_camera(const Camera* c, SceneBuilder& b) {
+    if (const DeviceExportable* e = dynamic_cast<const DeviceExportable*>(c)) { e->exportTo(b); return true; }
+#ifdef IPT_B200_REFERENCE_CLASSES
+    if (const SimpleCamera* sc = dynamic_cast<const SimpleCamera*>(c)) {
+        put(b.camera.position, sc->position);
+        put(b.camera.direction, sc->direction);
+        put(b.camera.right, sc->right);
+        put(b.camera.up, sc->up);
+        b.has_camera = true;
+        return true;
+    }
+#endif
+    return false;
 }
 
-ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, int device) {
-    const DeviceExportable* g = dynamic_cast<const DeviceExportable*>(scene.geometry.get());
+std::shared_ptr<DeviceContext> context_for(const Scene& scene, int device) {
+    SceneBuilder b;
     const DeviceExportable* l = dynamic_cast<const DeviceExportable*>(scene.lighting.get());
-    const DeviceExportable* c = dynamic_cast<const DeviceExportable*>(scene.camera.get());
-    if (!g || !l || !c)
+    if (!l || !export_geometry(scene.geometry.get(), b) || !export_camera(scene.camera.get(), b))
         throw Error(IPT_ERR_UNSUPPORTED,
-                    "ipt_b200::render_sample: every Scene member must be DeviceExportable (DeviceGeometry / DeviceLighting / "
-                    "DeviceCamera); the reference's own classes hide their data and there is no CPU fallback");
-    std::shared_ptr<DeviceContext> ctx;
-    {
-        std::lock_guard<std::mutex> lock(g_cache_mu);
-        auto key = std::make_tuple((const void*)scene.geometry.get(), (const void*)scene.lighting.get(), (const void*)scene.camera.get(), device);
-        auto it = g_cache.find(key);
-        if (it == g_cache.end()) {
-            SceneBuilder b;
-            g->exportTo(b);
-            l->exportTo(b);
-            c->exportTo(b);
-            it = g_cache.emplace(key, std::make_shared<DeviceContext>(b, device)).first;
-        }
-        ctx = it->second;
+                    "ipt_b200::render_sample: the Scene members must be DeviceExportable (DeviceGeometry / DeviceLighting / DeviceCamera) or, "
+                    "for geometry and camera in a build against the reference's headers, the reference's own data-free Geometry classes / "
+                    "SimpleCamera; other classes hide their data and there is no CPU fallback");
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    auto key = std::make_tuple((const void*)scene.geometry.get(), (const void*)scene.lighting.get(), (const void*)scene.camera.get(), device);
+    for (auto e = g_cache.begin(); e != g_cache.end();) e = e->second.alive() ? std::next(e) : g_cache.erase(e); // drop dead scenes
+    const DeviceExportable* ge = dynamic_cast<const DeviceExportable*>(scene.geometry.get());
+    const uint64_t grev = ge ? ge->revision() : 0, lrev = l->revision();
+    auto it = g_cache.find(key);
+    if (it != g_cache.end() && (it->second.geometry_revision != grev || it->second.lighting_revision != lrev)) { g_cache.erase(it); it = g_cache.end(); }
+    if (it == g_cache.end()) {
+        l->exportTo(b);
+        it = g_cache.emplace(key, CachedContext{scene.geometry, scene.lighting, scene.camera, std::make_shared<DeviceContext>(b, device), grev, lrev}).first;
     }
-    SceneBuilder cam;
-    c->exportTo(cam); // the camera may be orbited between calls (gui.cpp:107-137): always refresh it
-    check(ipt_scene_set_camera(ctx->scene(), &cam.camera));
-    ipt_render_stats stats{};
-    if (DevicePlane* dp = dynamic_cast<DevicePlane*>(&r_plane)) {
-        ipt_render_params p = params;
-        p.plane_mode = dp->plane_mode;
-        check(ipt_render(ctx->scene(), dp->attach(ctx), &p, &stats));
-        return stats;
-    }
-    // foreign RenderPlane: accumulate per loop pixel, then one addRay per pixel with the mean at the pixel centre
-    ipt_render_params p = params;
-    p.plane_mode = IPT_PLANE_LINEAR;
-    size_t n = (size_t)p.width * p.height;
-    std::vector<float> sum(n), sumsq(n);
-    std::vector<uint32_t> count(n);
-    check(ipt_render_host(ctx->scene(), &p, sum.data(), sumsq.data(), count.data(), &stats));
+    // the camera may be orbited between calls (gui.cpp:107-137): always refresh it
+    check(ipt_scene_set_camera(it->second.ctx->scene(), &b.camera));
+    return it->second.ctx;
+}
+
+// sum / count of loop-pixel cells -> a plane the library does not own
+void flush_foreign(RenderPlane& r_plane, const ipt_render_params& p, const std::vector<float>& sum, const std::vector<uint32_t>& count) {
     for (uint32_t iy = 0; iy < p.height; ++iy)
         for (uint32_t ix = 0; ix < p.width; ++ix) {
             size_t i = (size_t)iy * p.width + ix;
             if (count[i]) r_plane.addRay((ix + 0.5f) / p.width, (iy + 0.5f) / p.height, sum[i] / count[i]);
         }
+}
+
+#ifdef IPT_B200_REFERENCE_CLASSES
+// What count[i] calls of GridRenderPlane::addRay with values adding up to sum[i] leave in cell i (GridRenderPlane.cpp:68-74):
+// the running mean over old and new samples, the counter, and max_value over the cells written.
+void flush_grid(GridRenderPlane& g, const std::vector<float>& sum, const std::vector<uint32_t>& count) {
+    for (size_t i = 0; i < count.size(); ++i) {
+        if (!count[i]) continue;
+        size_t before = g.pixel_counters[i];
+        g.pixels[i] = before ? (g.pixels[i] * (float)before + sum[i]) / (float)(before + count[i]) : sum[i] / (float)count[i];
+        g.pixel_counters[i] = before + count[i];
+        if (g.pixels[i] > g.max_value) g.max_value = g.pixels[i];
+    }
+}
+#endif
+
+// contiguous, balanced pass ranges (the arithmetic of ipt_b200/sharding.py:shard_passes)
+void shard_passes(uint32_t total, size_t world, size_t rank, uint32_t first, uint32_t& begin, uint32_t& count) {
+    uint32_t base = total / (uint32_t)world, extra = total % (uint32_t)world;
+    count = base + (rank < extra ? 1u : 0u);
+    begin = first + (uint32_t)rank * base + (uint32_t)std::min<size_t>(rank, extra);
+}
+
+void add_stats(ipt_render_stats& a, const ipt_render_stats& b) {
+    a.paths += b.paths; a.rays += b.rays;
+    for (int d = 0; d < IPT_MAX_DEPTH; ++d) a.rays_at_depth[d] += b.rays_at_depth[d];
+    a.surface_hits += b.surface_hits; a.light_hits += b.light_hits; a.misses += b.misses;
+    a.failed_samples += b.failed_samples; a.zero_weight_pruned += b.zero_weight_pruned; a.nonfinite_dropped += b.nonfinite_dropped;
+    a.bvh_nodes_visited += b.bvh_nodes_visited; a.triangles_tested += b.triangles_tested; a.lights_tested += b.lights_tested;
+    a.light_bvh_nodes_visited += b.light_bvh_nodes_visited;
+    a.batches += b.batches; a.kernel_launches += b.kernel_launches;
+    a.ms_total = std::max(a.ms_total, b.ms_total); // the devices run side by side
+    a.queue_bytes += b.queue_bytes; a.rays_resolved_in_shade += b.rays_resolved_in_shade;
+}
+
+struct PlaneHandle { // a scratch plane on some device, destroyed with the scope
+    ipt_plane* p = nullptr;
+    ~PlaneHandle() { if (p) ipt_plane_destroy(p); }
+};
+} // namespace
+
+ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, int device) {
+    return render_sample(scene, r_plane, params, std::vector<int>{device});
+}
+
+ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, const std::vector<int>& devices) {
+    if (devices.empty()) throw Error(IPT_ERR_INVALID, "ipt_b200::render_sample: no device given");
+    DevicePlane* dp = dynamic_cast<DevicePlane*>(&r_plane);
+#ifdef IPT_B200_REFERENCE_CLASSES
+    GridRenderPlane* gp = dynamic_cast<GridRenderPlane*>(&r_plane);
+    if (gp && (gp->width != params.width || gp->height != params.height)) throw Error(IPT_ERR_INVALID, "GridRenderPlane size does not match render params");
+#else
+    const bool gp = false;
+#endif
+    ipt_render_params p = params;
+    p.plane_mode = dp ? dp->plane_mode : gp ? (uint32_t)IPT_PLANE_GRID : (uint32_t)IPT_PLANE_LINEAR;
+    const size_t world = devices.size();
+    std::vector<std::shared_ptr<DeviceContext>> ctx(world);
+    for (size_t r = 0; r < world; ++r) ctx[r] = context_for(scene, devices[r]); // scene replicas (cached per device)
+    // accumulators: device 0 renders into the caller's DevicePlane (or a scratch plane), the others into scratch planes
+    std::vector<PlaneHandle> scratch(world);
+    std::vector<ipt_plane*> plane(world, nullptr);
+    for (size_t r = 0; r < world; ++r) {
+        if (r == 0 && dp) plane[r] = dp->attach(ctx[0]);
+        else {
+            check(ipt_plane_create(ctx[r]->scene(), p.width, p.height, &scratch[r].p));
+            plane[r] = scratch[r].p;
+        }
+    }
+    std::vector<ipt_render_stats> st(world);
+    std::vector<std::string> err(world);
+    std::vector<int> code(world, IPT_OK);
+    auto work = [&](size_t r) {
+        ipt_render_params pr = p;
+        shard_passes(p.pass_count, world, r, p.pass_begin, pr.pass_begin, pr.pass_count);
+        std::memset(&st[r], 0, sizeof st[r]);
+        if (pr.pass_count == 0) return;
+        int rc = ipt_render(ctx[r]->scene(), plane[r], &pr, &st[r]);
+        if (rc != IPT_OK) { code[r] = rc; err[r] = ipt_last_error(); } // ipt_last_error is per thread: fetch it here
+    };
+    if (world == 1) work(0);
+    else {
+        std::vector<std::thread> threads;
+        for (size_t r = 0; r < world; ++r) threads.emplace_back(work, r);
+        for (std::thread& t : threads) t.join();
+    }
+    for (size_t r = 0; r < world; ++r)
+        if (code[r] != IPT_OK) throw Error(code[r], "ipt_b200: device " + std::to_string(devices[r]) + ": " + err[r]);
+    ipt_render_stats stats = st[0];
+    for (size_t r = 1; r < world; ++r) {
+        check(ipt_plane_merge(plane[0], plane[r])); // the only exchange: 12 B per cell and device
+        add_stats(stats, st[r]);
+    }
+    if (dp) return stats;
+    // a plane the library does not own: read the accumulators back once and write the caller's plane
+    size_t n = (size_t)p.width * p.height;
+    std::vector<float> sum(n), sumsq(n);
+    std::vector<uint32_t> count(n);
+    check(ipt_plane_download(plane[0], sum.data(), sumsq.data(), count.data()));
+#ifdef IPT_B200_REFERENCE_CLASSES
+    if (gp) { flush_grid(*gp, sum, count); return stats; }
+#endif
+    flush_foreign(r_plane, p, sum, count);
     return stats;
 }
 

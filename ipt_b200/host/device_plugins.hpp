@@ -47,6 +47,9 @@ struct SceneBuilder {
 };
 struct DeviceExportable {
     virtual void exportTo(SceneBuilder& b) const = 0;
+    // bumped by every mutation that changes what exportTo() writes (cameras excepted: they are re-read on every call), so
+    // that render_sample's cached device replica of the scene is rebuilt when an object was edited after a render
+    virtual uint64_t revision() const { return 0; }
     virtual ~DeviceExportable() {}
 };
 
@@ -77,9 +80,11 @@ public:
 
     std::optional<surface_intersection> traceRay(glm::vec3 origin, glm::vec3 direction) const override;
     void exportTo(SceneBuilder& b) const override;
+    uint64_t revision() const override { return revision_; }
 
 private:
     friend class DeviceSdf;
+    uint64_t revision_ = 0;
     SceneBuilder data_;
     mutable std::shared_ptr<DeviceContext> ctx_; // geometry-only context used by traceRay()
     mutable std::mutex mu_;
@@ -94,7 +99,8 @@ public:
     void addSquareLight(glm::vec3 corner, glm::vec3 normal, glm::vec3 x_side, float power = 1.0f);
     void addTriangleLight(glm::vec3 corner, glm::vec3 x_side, glm::vec3 y_side, float power = 1.0f);
     void addOuterLight(float radius, float power = 1.0f);
-    void addLight(const ipt_light& l) { lights_.push_back(l); ctx_.reset(); }
+    void addLight(const ipt_light& l) { lights_.push_back(l); ctx_.reset(); ++revision_; }
+    uint64_t revision() const override { return revision_; }
     size_t size() const { return lights_.size(); }
 
     std::unique_ptr<Ddf> distributionInPoint(glm::vec3 pos) const override;
@@ -103,6 +109,7 @@ public:
 
 private:
     friend class DeviceLightDdf;
+    uint64_t revision_ = 0;
     std::vector<ipt_light> lights_;
     mutable std::shared_ptr<DeviceContext> ctx_;
     mutable std::mutex mu_;
@@ -160,10 +167,25 @@ inline Scene make_scene_lit_corner() { return make_scene("corner"); }
 
 // ---- the hot path ------------------------------------------------------------------------------------------
 // params.pass_count calls of the reference's render_sample(scene, r_plane, stats) (src/main.cpp:186-223).
-// Every Scene member must be DeviceExportable (dynamic_cast, the reference's own idiom: gui.cpp:58, ddf.cpp:177);
-// otherwise this throws -- it never falls back to tracing on the CPU.
-// A DevicePlane receives the accumulators directly. Any other RenderPlane receives ONE addRay(x_centre, y_centre,
-// mean) per cell (documented approximation: `count` samples collapse into one call).
+//
+// Scene members are discovered by dynamic_cast, the reference's own idiom (gui.cpp:58, ddf.cpp:177):
+//   * anything DeviceExportable (the classes above);
+//   * built against the REFERENCE's headers (IPT_B200_REFERENCE_CLASSES: src/ is on the include path), also the reference's
+//     own objects where they expose what the device needs: SimpleCamera (public position / direction / right / up,
+//     SimpleCamera.h:11-13) and the six data-free Geometry classes, whose primitive lists are literals inside traceRay()
+//     (GeometrySphereInBox.cpp:11-17, ...) and are restated in ipt_sample_scene. Lighting must be a DeviceLighting:
+//     AreaLight keeps its axes private (lighting.h:20-23).
+// Anything else throws -- it never falls back to tracing on the CPU.
+//
+// The plane: a DevicePlane receives the accumulators directly. A reference GridRenderPlane (reference headers) is written
+// the way addRay would have left it: pixels[i] = running mean, pixel_counters[i] += samples, max_value, cells by
+// GridRenderPlane::addRay's own mapping (GridRenderPlane.cpp:61-75). Any other RenderPlane receives ONE
+// addRay(x_centre, y_centre, mean) per cell (documented approximation: `count` samples collapse into one call).
 ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, int device = 0);
+// The same job on several GPUs of this process: one host thread per device (the shape of the reference's own driver,
+// main.cpp:258-277: N threads, one plane), each rendering a contiguous share of params.pass_count passes of the whole
+// frame on its own replica of the scene; the per-device accumulators are merged into the plane of devices[0] with
+// ipt_plane_merge (peer copy + add on the device). The result equals the single-device render of the same passes.
+ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, const std::vector<int>& devices);
 
 } // namespace ipt_b200

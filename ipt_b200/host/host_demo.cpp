@@ -60,6 +60,26 @@ int main(int argc, char** argv) {
         cam->orbit(IPT_KEY_LEFT);
         cam->orbit(IPT_KEY_RIGHT);
         float orbit_err = std::fabs(cam->position.x - before.x) + std::fabs(cam->position.y - before.y) + std::fabs(cam->position.z - before.z);
+        // the multi-GPU entry: the same passes split over two device slots (two GPUs when the box has them), merged on the
+        // device by ipt_plane_merge, must reproduce the single-device plane
+        ipt_b200::DevicePlane mplane(96, 96);
+        std::vector<int> slots = {0, ipt_device_count() > 1 ? 1 : 0};
+        ipt_render_stats mst = ipt_b200::render_sample(scene, mplane, p, slots);
+        mplane.download();
+        std::vector<float> s1, q1, s2, q2;
+        std::vector<uint32_t> c1, c2;
+        dplane.sums(s1, q1, c1);
+        mplane.sums(s2, q2, c2);
+        size_t multi_counters_equal = 0;
+        double multi_max_rel = 0;
+        for (size_t i = 0; i < c1.size(); ++i) {
+            multi_counters_equal += c1[i] == c2[i];
+            double scale = std::fabs(s1[i]) > 1e-6 ? std::fabs(s1[i]) : 1e-6;
+            double rel = std::fabs((double)s1[i] - s2[i]) / scale;
+            if (rel > multi_max_rel) multi_max_rel = rel;
+        }
+        printf("{\"multi_devices\": [%d, %d], \"multi_paths\": %llu, \"multi_rays\": %llu, \"multi_counters_equal\": %zu, \"multi_max_rel\": %.3g}\n", slots[0],
+               slots[1], (unsigned long long)mst.paths, (unsigned long long)mst.rays, multi_counters_equal, multi_max_rel);
         dplane.addRay(0.5f, 0.5f, 1.0f);
         printf("{\"display_max\": %.9g, \"orbit_round_trip_error\": %.9g}\n", shown_max, orbit_err);
         printf("{\"scene\": \"%s\", \"paths\": %llu, \"rays\": %llu, \"mean_device_plane\": %.9g, \"count_device_plane\": %zu, "

@@ -10,10 +10,19 @@
 //   3. compares, ray by ray, Geometry::traceRay / Lighting::traceRayToLight of the two object sets (must be equal to
 //      the bit) and the mean estimate over the same camera rays (statistical: the DDF samples come from different
 //      random generators).
+//   4. renders through ipt_b200::render_sample a Scene made of the REFERENCE's own objects where they expose their data —
+//      the reference's GeometrySphereInBox and SimpleCamera (constructed here, as sample_scenes.cpp:20-41 does) with a
+//      DeviceLighting carrying the same light — into a reference GridRenderPlane, and compares that plane (pixels,
+//      pixel_counters, max_value) with a DevicePlane rendered from ipt_b200's own classes: same cells, same counters, same
+//      means; then the same job split over two device slots (the multi-GPU entry) must reproduce it.
 // Prints one JSON object; tests/test_host_cpp.py checks it on the GPU box.
 #include "device_plugins.hpp"
 
+#include <GridRenderPlane.h>
 #include <SimpleCamera.h>
+#include <geometry/GeometrySphereInBox.h>
+
+#include <glm/geometric.hpp>
 
 #include <cmath>
 #include <cstdio>
@@ -78,9 +87,51 @@ int main(int argc, char** argv) {
         }
         double m_ref = sum_ref / rays, m_ours = sum_ours / rays;
         double se = std::sqrt((sq_ref / rays - m_ref * m_ref + sq_ours / rays - m_ours * m_ours) / rays);
+        // ---- 4. the reference's own objects through ipt_b200::render_sample -------------------------------------------
+        size_t cells_equal = 0, cells = 0, counters_equal = 0;
+        double max_rel = 0, max_rel_multi = 0;
+        float max_value_grid = 0, max_value_device = 0;
+        int devices_seen = ipt_device_count();
+        if (std::strcmp(name, "box") == 0) {
+            // make_scene_box (sample_scenes.cpp:20-41) with the reference's geometry and camera classes
+            glm::vec3 camera_pos(0.0f, -3.0f, 0.1f);
+            glm::vec3 camera_dir = glm::normalize(glm::vec3(0.0f, 1.0f, -1.0f) - camera_pos);
+            auto lighting = std::make_shared<ipt_b200::DeviceLighting>();
+            lighting->addSquareLight(glm::vec3{+0.1f, -0.8f - 0.1f, -0.15f}, glm::vec3(0.0f, 0.0f, -1.0f), glm::vec3{0.0f, 0.2f, 0.0f}, 1.0f);
+            Scene mixed{std::make_shared<GeometrySphereInBox>(), lighting, std::make_shared<SimpleCamera>(camera_pos, camera_dir)};
+            ipt_render_params p;
+            ipt_render_params_default(&p);
+            p.width = p.height = 80;
+            p.pass_count = 6;
+            p.seed = 17;
+            GridRenderPlane grid(80, 80);
+            ipt_b200::render_sample(mixed, grid, p);
+            ipt_b200::DevicePlane dplane(80, 80);
+            ipt_b200::render_sample(ours, dplane, p);
+            dplane.download();
+            GridRenderPlane grid2(80, 80); // the same passes on two device slots, merged by ipt_plane_merge
+            std::vector<int> two = {0, devices_seen > 1 ? 1 : 0};
+            ipt_b200::render_sample(mixed, grid2, p, two);
+            for (size_t i = 0; i < grid.pixels.size(); ++i) {
+                counters_equal += grid.pixel_counters[i] == dplane.pixel_counters[i] && grid2.pixel_counters[i] == dplane.pixel_counters[i];
+                if (!dplane.pixel_counters[i]) continue;
+                ++cells;
+                double scale = std::fabs(dplane.pixels[i]) > 1e-6 ? std::fabs(dplane.pixels[i]) : 1e-6;
+                double rel = std::fabs((double)grid.pixels[i] - dplane.pixels[i]) / scale;
+                double rel2 = std::fabs((double)grid2.pixels[i] - dplane.pixels[i]) / scale;
+                cells_equal += rel <= 1e-5;
+                if (rel > max_rel) max_rel = rel;
+                if (rel2 > max_rel_multi) max_rel_multi = rel2;
+            }
+            max_value_grid = grid.max_value;
+            max_value_device = dplane.max_value;
+        }
         printf("{\"scene\": \"%s\", \"rays\": %d, \"geometry_equal\": %zu, \"geometry_hits\": %zu, \"light_equal\": %zu, \"light_hits\": %zu, "
-               "\"mean_reference_objects\": %.9g, \"mean_ipt_b200_objects\": %.9g, \"standard_error\": %.9g}\n",
-               name, rays, geometry_equal, hits, light_equal, lhits, m_ref, m_ours, se);
+               "\"mean_reference_objects\": %.9g, \"mean_ipt_b200_objects\": %.9g, \"standard_error\": %.9g, "
+               "\"grid_cells\": %zu, \"grid_cells_equal\": %zu, \"grid_counters_equal\": %zu, \"grid_max_rel\": %.3g, \"grid_max_rel_two_devices\": %.3g, "
+               "\"grid_max_value\": %.9g, \"device_max_value\": %.9g, \"devices\": %d}\n",
+               name, rays, geometry_equal, hits, light_equal, lhits, m_ref, m_ours, se, cells, cells_equal, counters_equal, max_rel, max_rel_multi,
+               max_value_grid, max_value_device, devices_seen);
     } catch (const ipt_b200::Error& e) {
         printf("{\"error\": \"%s\", \"code\": %d}\n", e.what(), e.code);
         return e.code == IPT_ERR_NO_DEVICE ? 3 : 1;

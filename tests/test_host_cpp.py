@@ -42,7 +42,8 @@ def test_render_sample_through_the_cpp_interfaces(scene, host_demo, oracle, tmp_
     png = tmp_path / "result.png"
     r = subprocess.run([str(host_demo), scene, "4", str(png)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    first, last = r.stdout.strip().splitlines()
+    multi, first, last = r.stdout.strip().splitlines()
+    multi = json.loads(multi)   # ipt_b200::render_sample(scene, plane, params, devices): same passes on two device slots
     stage = json.loads(first)
     assert stage["display_max"] == 1.0 and stage["orbit_round_trip_error"] < 1e-5   # DevicePlane::display, DeviceCamera::orbit
     from test_output_host import decode_png_gray8
@@ -50,6 +51,8 @@ def test_render_sample_through_the_cpp_interfaces(scene, host_demo, oracle, tmp_
     assert img.shape == (96, 96) and img.max() == 255 and len(np.unique(img)) > 30
     out = json.loads(last)
     assert out["paths"] == 96 * 96 * 4 and out["rays"] > out["paths"]
+    assert multi["multi_paths"] == out["paths"] and multi["multi_rays"] == out["rays"]
+    assert multi["multi_counters_equal"] == 96 * 96 and multi["multi_max_rel"] < 2e-5     # float atomics order only
     sd = capi.SceneDescription(scene)
     p = capi.default_params(width=96, height=96, pass_count=4)
     o = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 0)
@@ -96,3 +99,8 @@ def test_reference_estimator_runs_on_ipt_b200_objects(lib):
     assert out["light_equal"] == out["rays"] and out["light_hits"] > 50
     assert abs(out["mean_reference_objects"] - out["mean_ipt_b200_objects"]) < 4 * out["standard_error"] + 1e-4
     assert out["mean_reference_objects"] > 0
+    # the reference's GeometrySphereInBox + SimpleCamera + GridRenderPlane through ipt_b200::render_sample == DevicePlane
+    assert out["grid_cells"] > 0.9 * 80 * 80 and out["grid_counters_equal"] == 80 * 80
+    assert out["grid_cells_equal"] == out["grid_cells"] and out["grid_max_rel"] <= 1e-5
+    assert out["grid_max_rel_two_devices"] < 2e-5
+    assert abs(out["grid_max_value"] - out["device_max_value"]) <= 1e-5 * out["device_max_value"]
