@@ -261,6 +261,12 @@ typedef struct ipt_bvh_node {
     uint32_t pad;
 } ipt_bvh_node;
 int ipt_bvh_export(ipt_scene* scene, ipt_bvh_node* nodes, uint32_t* sorted_prims, uint64_t* morton, uint64_t* n_nodes);
+/* The same tree in the form the traversal kernels read: 32 bytes per node = both children's boxes on a 16-bit grid over
+ * the root box (rounded outwards by one extra cell: conservative) + the two child ids. 8 uint32 per node:
+ * lo0.x|lo0.y<<16, lo0.z|hi0.x<<16, hi0.y|hi0.z<<16, lo1.x|lo1.y<<16, lo1.z|hi1.x<<16, hi1.y|hi1.z<<16, left, right.
+ * grid[0..2] = lower corner of the root box, grid[3..5] = (1 - 2^-13) / extent: a world coordinate x sits at grid
+ * coordinate (x - lo) * scale * 65536 + 4. Integer work + three float steps: byte-identical to the CPU restatement. */
+int ipt_bvh_export_compact(ipt_scene* scene, uint32_t* nodes32, float grid[6], uint64_t* n_nodes);
 
 /* ---- render plane: replaces RenderPlane::addRay accumulation (tracer_interfaces.h:51-54) --------- */
 int ipt_plane_create(ipt_scene* scene, uint32_t width, uint32_t height, ipt_plane** out);

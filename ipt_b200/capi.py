@@ -109,6 +109,7 @@ SIGNATURES = {
     "ipt_light_ddf_sample": (C.c_int, [_vp, f32p, C.c_uint64, C.c_size_t, f32p]),
     "ipt_philox_batch": (C.c_int, [C.c_int, u32p, C.c_size_t, C.c_uint64, u32p, f32p]),
     "ipt_bvh_export": (C.c_int, [_vp, C.POINTER(BvhNode), u32p, u64p, u64p]),
+    "ipt_bvh_export_compact": (C.c_int, [_vp, u32p, f32p, u64p]),
     "ipt_plane_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
     "ipt_plane_wrap": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
     "ipt_plane_clear": (C.c_int, [_vp]),
@@ -338,6 +339,14 @@ class Scene:
         nodes = np.zeros(n, BVH_NODE_DTYPE); order = np.empty(ntri, np.uint32); keys = np.empty(ntri, np.uint64)
         check(load().ipt_bvh_export(self.handle, nodes.ctypes.data_as(C.POINTER(BvhNode)), _ptr(order, u32p), _ptr(keys, u64p), C.byref(n_nodes)))
         return nodes, order, keys
+
+    def bvh_export_compact(self):
+        """(nodes uint32[n-1, 8], grid float32[6]): the 32-byte traversal nodes and their world -> grid map."""
+        n = C.c_uint64(0)
+        check(load().ipt_bvh_export_compact(self.handle, None, None, C.byref(n)))
+        nodes = np.zeros((n.value, 8), np.uint32); grid = np.zeros(6, np.float32)
+        check(load().ipt_bvh_export_compact(self.handle, _ptr(nodes, u32p), _ptr(grid, f32p), C.byref(n)))
+        return nodes, grid
 
     def render_host(self, params: RenderParams, out=None):
         """The end-to-end call: host buffers in, host buffers out. `out` = (sum, sumsq, count) arrays to reuse."""

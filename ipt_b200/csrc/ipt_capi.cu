@@ -554,6 +554,8 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
         dv.tris = s->bvh.tri_records;
         dv.tri_id = s->bvh.sorted_ids;
         dv.nodes = s->bvh.nodes;
+        dv.qnodes = s->bvh.qnodes;
+        dv.grid = s->bvh.grid;
     }
     // many area lights: LBVH over them (nearest-light and all-hits density queries instead of O(L) scans)
     {
@@ -824,6 +826,19 @@ int ipt_bvh_export(ipt_scene* s, ipt_bvh_node* nodes, uint32_t* sorted_prims, ui
     if (nodes && n > 1) CUDA_TRY(cudaMemcpy(nodes, s->bvh.nodes, sizeof(BvhNode) * (n - 1), cudaMemcpyDeviceToHost));
     if (sorted_prims) CUDA_TRY(cudaMemcpy(sorted_prims, s->bvh.sorted_ids, 4 * (size_t)n, cudaMemcpyDeviceToHost));
     if (morton) CUDA_TRY(cudaMemcpy(morton, s->bvh.sorted_keys, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    return IPT_OK;
+}
+
+int ipt_bvh_export_compact(ipt_scene* s, uint32_t* nodes32, float grid[6], uint64_t* n_nodes) {
+    if (!s) return fail(IPT_ERR_INVALID, "null scene");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    if (!s->mesh) return fail(IPT_ERR_INVALID, "scene has no triangle mesh");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    uint32_t n = s->bvh.n;
+    if (n_nodes) *n_nodes = n > 1 ? n - 1 : 0;
+    if (nodes32 && n > 1) CUDA_TRY(cudaMemcpy(nodes32, s->bvh.qnodes, sizeof(BvhNodeQ) * (size_t)(n - 1), cudaMemcpyDeviceToHost));
+    if (grid) for (int a = 0; a < 3; ++a) { grid[a] = s->bvh.grid.lo[a]; grid[3 + a] = s->bvh.grid.scale[a]; }
     return IPT_OK;
 }
 

@@ -31,6 +31,9 @@
 #define IPT_EXTEND_MIN_BLOCKS 3
 #endif
 #include <cstdio>
+#ifndef IPT_LIGHT_TWO_QUEUES
+#define IPT_LIGHT_TWO_QUEUES 1 // 0: one park queue for every child of a many-light scene (tuning A/B only)
+#endif
 #ifndef IPT_FAST_SECONDARY
 #define IPT_FAST_SECONDARY 1 // rays of depth >= 1 use the contracted arithmetic (tdot3 / tpoint<false>), see DESIGN.md section 2
 #endif
@@ -579,7 +582,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
     constexpr int PARK_WORDS = 9;
     // many-light scenes, non-last depths: children are regrouped by whether they can see a light at all (the root boxes of
     // the light LBVH): the ones that can walk the LBVH 32 at a time, the others only intersect the geometry
-    constexpr bool TWO_Q = FUSE == FUSE_NEXT && SPEC == SPEC_LIGHT_BVH;
+    constexpr bool TWO_Q = FUSE == FUSE_NEXT && SPEC == SPEC_LIGHT_BVH && IPT_LIGHT_TWO_QUEUES;
     constexpr int QUEUES = TWO_Q ? 2 : 1;
     __shared__ float dq_all[FUSE != FUSE_NONE ? (256 / 32) * PARK_WORDS * IPT_PARK * QUEUES : 1];
     float* dq = dq_all + (FUSE != FUSE_NONE ? (threadIdx.x >> 5) * PARK_WORDS * IPT_PARK * QUEUES : 0); // this warp's parked rays

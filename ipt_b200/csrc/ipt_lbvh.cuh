@@ -7,6 +7,7 @@
 #pragma once
 #include "ipt_device.cuh"
 
+#include <cmath>
 #include <string>
 
 namespace iptd {
@@ -17,6 +18,8 @@ struct LbvhDevice {
     uint32_t* sorted_ids = nullptr;      // sorted position -> original index
     unsigned long long* sorted_keys = nullptr; // 63-bit Morton keys, ascending
     BvhNode* nodes = nullptr;            // n-1 internal nodes, root = 0
+    BvhNodeQ* qnodes = nullptr;          // the same nodes in the 32-byte traversal form
+    GridMap grid{};                      // world -> grid space of qnodes
 };
 
 // order-preserving float <-> uint map for atomicMin/atomicMax
@@ -276,8 +279,32 @@ __global__ void k_lbvh_records(const float* __restrict__ tris, const uint32_t* _
     rec[4 * (size_t)k + 3] = make_float4(__uint_as_float(ids[k]), ex ? ex[0] : 1.0f, ex ? ex[1] : 0.0f, ex ? ex[2] : 0.0f);
 }
 
+// 64-byte node -> 32-byte node (see BvhNodeQ): one thread per node. Low bounds round down, high bounds up, then one more
+// cell outwards. Float steps: (x - lo) with __fsub_rn, then one __fmaf_rn — oracle/ipt_oracle_mesh.inc restates them.
+__device__ __forceinline__ uint32_t grid_quant(float x, float lo, float scale, bool upper) {
+    float g = __fmaf_rn(__fsub_rn(x, lo), scale, IPT_GRID_BASE);
+    g = fminf(fmaxf(g, 1.0f), 1.99993896484375f);
+    uint32_t m = __float_as_uint(g) & 0x007FFFFFu; // 23-bit mantissa of a float in [1, 2)
+    int q = upper ? (int)((m + 127u) >> 7) + 1 : (int)(m >> 7) - 1;
+    return (uint32_t)min(max(q, 0), 65535);
+}
+__global__ void k_lbvh_compact(const BvhNode* __restrict__ nodes, uint32_t n_nodes, GridMap G, BvhNodeQ* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    BvhNode nd = nodes[i];
+    uint32_t l0x = grid_quant(nd.lo0x, G.lo[0], G.scale[0], false), l0y = grid_quant(nd.lo0y, G.lo[1], G.scale[1], false), l0z = grid_quant(nd.lo0z, G.lo[2], G.scale[2], false);
+    uint32_t h0x = grid_quant(nd.hi0x, G.lo[0], G.scale[0], true), h0y = grid_quant(nd.hi0y, G.lo[1], G.scale[1], true), h0z = grid_quant(nd.hi0z, G.lo[2], G.scale[2], true);
+    uint32_t l1x = grid_quant(nd.lo1x, G.lo[0], G.scale[0], false), l1y = grid_quant(nd.lo1y, G.lo[1], G.scale[1], false), l1z = grid_quant(nd.lo1z, G.lo[2], G.scale[2], false);
+    uint32_t h1x = grid_quant(nd.hi1x, G.lo[0], G.scale[0], true), h1y = grid_quant(nd.hi1y, G.lo[1], G.scale[1], true), h1z = grid_quant(nd.hi1z, G.lo[2], G.scale[2], true);
+    BvhNodeQ q;
+    q.w[0] = l0x | (l0y << 16); q.w[1] = l0z | (h0x << 16); q.w[2] = h0y | (h0z << 16);
+    q.w[3] = l1x | (l1y << 16); q.w[4] = l1z | (h1x << 16); q.w[5] = h1y | (h1z << 16);
+    q.w[6] = nd.left; q.w[7] = nd.right;
+    out[i] = q;
+}
+
 static inline void lbvh_free(LbvhDevice& b) {
-    cudaFree(b.tri_records); cudaFree(b.sorted_ids); cudaFree(b.sorted_keys); cudaFree(b.nodes);
+    cudaFree(b.tri_records); cudaFree(b.sorted_ids); cudaFree(b.sorted_keys); cudaFree(b.nodes); cudaFree(b.qnodes);
     b = LbvhDevice();
 }
 
@@ -337,6 +364,19 @@ static inline int lbvh_build(const float* host_tris, uint32_t n, cudaStream_t st
             LB_TRY(cudaMemsetAsync(d_flags, 0, 4 * (size_t)n, st));
             k_lbvh_hierarchy<<<blocks, 256, 0, st>>>(out.sorted_keys, n, out.nodes, d_leaf_parent);
             k_lbvh_refit<<<blocks, 256, 0, st>>>(d_lo, d_hi, out.sorted_ids, n, out.nodes, d_leaf_parent, d_flags);
+            // the grid of the 32-byte nodes spans the root box = the union of the root's two child boxes
+            BvhNode root;
+            LB_TRY(cudaMemcpyAsync(&root, out.nodes, sizeof root, cudaMemcpyDeviceToHost, st));
+            LB_TRY(cudaStreamSynchronize(st));
+            const float rlo[3] = {std::fmin(root.lo0x, root.lo1x), std::fmin(root.lo0y, root.lo1y), std::fmin(root.lo0z, root.lo1z)};
+            const float rhi[3] = {std::fmax(root.hi0x, root.hi1x), std::fmax(root.hi0y, root.hi1y), std::fmax(root.hi0z, root.hi1z)};
+            for (int a = 0; a < 3; ++a) {
+                float ext = rhi[a] - rlo[a];
+                out.grid.lo[a] = rlo[a];
+                out.grid.scale[a] = ext > 0.0f ? IPT_GRID_FILL / ext : 1.0f; // a flat scene: every coordinate maps to 1
+            }
+            LB_TRY(cudaMalloc((void**)&out.qnodes, sizeof(BvhNodeQ) * (size_t)(n - 1)));
+            k_lbvh_compact<<<(n - 1 + 255) / 256, 256, 0, st>>>(out.nodes, n - 1, out.grid, out.qnodes);
         }
         LB_TRY(cudaGetLastError());
         LB_TRY(cudaStreamSynchronize(st));

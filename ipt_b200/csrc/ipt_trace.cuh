@@ -42,6 +42,42 @@ __device__ __forceinline__ float slab(float lox, float loy, float loz, float hix
     return (tn <= tf * 1.0000003f && tn <= best) ? tn : IPT_INF;
 }
 
+// ---- traversal of the 32-byte nodes (BvhNodeQ) in grid space ------------------------------------------------------------
+// A ray is mapped once: entry / exit distances of a slab at grid coordinate g are  t = g * inv + c  with inv = 1 / d' and
+// c = -o' * inv. t is the world-space ray parameter (GridMap), so it compares directly with the best hit distance. The
+// quantised boxes are a full grid cell (1.5e-5) larger than the float boxes on every side; the float error of the mapped
+// ray and of the fused multiply-add is below 1e-6 grid units, so the test stays conservative. An axis with d == 0
+// yields NaN and drops out of the fminf / fmaxf chain (the axis then does not constrain: conservative).
+#ifndef IPT_BVH_WIDE_NODES
+#define IPT_BVH_WIDE_NODES 0 // 1: traverse the 64-byte float nodes instead (tuning A/B only)
+#endif
+struct GridRay {
+    f3 inv, c;
+};
+__device__ __forceinline__ GridRay grid_ray(const GridMap& G, f3 o, f3 d) {
+    GridRay r;
+#if IPT_BVH_WIDE_NODES
+    r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.c = o;
+    return r;
+#endif
+    float ox = __fmaf_rn(__fsub_rn(o.x, G.lo[0]), G.scale[0], IPT_GRID_BASE), oy = __fmaf_rn(__fsub_rn(o.y, G.lo[1]), G.scale[1], IPT_GRID_BASE),
+          oz = __fmaf_rn(__fsub_rn(o.z, G.lo[2]), G.scale[2], IPT_GRID_BASE);
+    r.inv = mk3(1.0f / (d.x * G.scale[0]), 1.0f / (d.y * G.scale[1]), 1.0f / (d.z * G.scale[2]));
+    r.c = mk3(-ox * r.inv.x, -oy * r.inv.y, -oz * r.inv.z);
+    return r;
+}
+__device__ __forceinline__ float slab_q(uint32_t wa, uint32_t wb, uint32_t wc, const GridRay& R, float best) {
+    // wa = lo.x | lo.y, wb = lo.z | hi.x, wc = hi.y | hi.z
+    float t0x = __fmaf_rn(grid_lo16(wa), R.inv.x, R.c.x), t1x = __fmaf_rn(grid_hi16(wb), R.inv.x, R.c.x);
+    float t0y = __fmaf_rn(grid_hi16(wa), R.inv.y, R.c.y), t1y = __fmaf_rn(grid_lo16(wc), R.inv.y, R.c.y);
+    float t0z = __fmaf_rn(grid_lo16(wb), R.inv.z, R.c.z), t1z = __fmaf_rn(grid_hi16(wc), R.inv.z, R.c.z);
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    return (tn <= tf * 1.0000003f && tn <= best) ? tn : IPT_INF;
+}
+// second child: words 3..5 hold lo1.x | lo1.y, lo1.z | hi1.x, hi1.y | hi1.z — the same layout
+
 __device__ __forceinline__ void test_triangle(const DevScene& S, uint32_t pos, f3 o, f3 d, float& best_t, uint32_t& best_orig,
                                               uint32_t& best_pos, bool best_is_tri, TraceCounters& tc) {
     f8 r0 = ldg256(&S.tris[4 * (size_t)pos]);
@@ -72,18 +108,26 @@ __device__ __forceinline__ bool bvh_closest(const DevScene& S, f3 o, f3 d, float
         t_out = best_t; orig_out = best_orig; pos_out = best_pos;
         return true;
     }
-    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const GridRay R = grid_ray(S.grid, o, d);
     TravStack st;
     st.sm = smem_stack + threadIdx.x;
     st.n = 0;
     uint32_t node = 0;
     while (true) {
+#if IPT_BVH_WIDE_NODES
         f8 n0 = ldg256(&S.nodes[node]);
         f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
         ++tc.nodes;
         uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
-        float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], o, inv, best_t);
-        float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], o, inv, best_t);
+        float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], R.c, R.inv, best_t);
+        float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], R.c, R.inv, best_t);
+#else
+        u8x32 q = ldg256u(&S.qnodes[node]);
+        ++tc.nodes;
+        uint32_t left = q.v[6], right = q.v[7];
+        float tn0 = slab_q(q.v[0], q.v[1], q.v[2], R, best_t);
+        float tn1 = slab_q(q.v[3], q.v[4], q.v[5], R, best_t);
+#endif
         uint32_t next = IPT_NO_HIT;
         bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
         // leaves are intersected immediately; inner children are visited nearer-first
@@ -206,7 +250,9 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
     TraceCounters tc{0, 0, 0, 0};
     bool have = false, trav = false, exhausted = false;
     float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
-    f3 inv = mk3(0, 0, 0), lpos = mk3(0, 0, 0);
+    GridRay R;
+    R.inv = mk3(0, 0, 0); R.c = mk3(0, 0, 0);
+    f3 lpos = mk3(0, 0, 0);
     float a_t = IPT_INF, best_t = IPT_INF, sv = -1.0f, ldist = 0.0f;
     uint32_t a_prim = IPT_NO_HIT, best_orig = IPT_NO_HIT, best_pos = IPT_NO_HIT, lwhich = IPT_NO_HIT, node = 0, pend = IPT_NO_HIT;
     TravStack st;
@@ -248,7 +294,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                         test_triangle(S, 0, o, d, best_t, best_orig, best_pos, false, tc);
                         trav = false;
                     } else {
-                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        R = grid_ray(S.grid, o, d);
                         node = 0; pend = IPT_NO_HIT; st.n = 0; trav = true;
                     }
                 }
@@ -265,13 +311,20 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
         for (int step = 0; step < IPT_TRAV_STEPS; ++step) {
             if (have && trav) {
                 if (node != IPT_NO_HIT && pend == IPT_NO_HIT) {
-                    f3 o = mk3(ro.x, ro.y, ro.z);
+#if IPT_BVH_WIDE_NODES
                     f8 n0 = ldg256(&S.nodes[node]);
                     f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
                     ++tc.nodes;
                     uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
-                    float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], o, inv, best_t);
-                    float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], o, inv, best_t);
+                    float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], R.c, R.inv, best_t);
+                    float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], R.c, R.inv, best_t);
+#else
+                    u8x32 q = ldg256u(&S.qnodes[node]);
+                    ++tc.nodes;
+                    uint32_t left = q.v[6], right = q.v[7];
+                    float tn0 = slab_q(q.v[0], q.v[1], q.v[2], R, best_t);
+                    float tn1 = slab_q(q.v[3], q.v[4], q.v[5], R, best_t);
+#endif
                     bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
                     if (h0 && (left & 0x80000000u)) { pend = left; h0 = false; }
                     if (h1 && (right & 0x80000000u)) {

@@ -221,6 +221,12 @@ class Oracle(_OutputStage):
         self.lib.ipt_oracle_bvh_build(_p(t, f32p), C.c_uint64(n), nodes.ctypes.data_as(C.c_void_p), _p(ids, u32p), _p(keys, u64p))
         return nodes, ids, keys
 
+    def bvh_compact(self, nodes):
+        """The 32-byte traversal nodes derived from the 64-byte ones (k_lbvh_compact): (uint32[n, 8], grid float32[6])."""
+        out = np.zeros((len(nodes), 8), np.uint32); grid = np.zeros(6, np.float32)
+        self.lib.ipt_oracle_bvh_compact(nodes.ctypes.data_as(C.c_void_p), C.c_uint64(len(nodes)), _p(out, u32p), _p(grid, f32p))
+        return out, grid
+
     def philox_rounds(self, rounds, c, k):
         out = (C.c_uint32 * 4)()
         self.lib.ipt_oracle_philox_rounds(rounds, *[C.c_uint32(v) for v in c], *[C.c_uint32(v) for v in k], out)

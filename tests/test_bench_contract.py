@@ -22,6 +22,9 @@ def test_reference_arm_prints_the_contract_line(ref):
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "weak"
     assert "configs[1]" in d["config"]["workload"] and d["value"] > 0 and d["ms_per_step"] > 0
+    # the line says itself that the CPU leg renders a sample frame, not the 1024x1024 job
+    assert d["config"]["same_config"] is False and d["config"]["sample_width"] == 128 and d["config"]["job_width"] == 1024
+    assert "128x128 sample frame" in d["config"]["workload"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "128x128" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -138,7 +138,10 @@ def test_c4_ten_million_triangles_bit_exact(lib, oracle):
     cn, cids, ckeys = oracle.bvh_build(sd.triangles())
     assert np.array_equal(keys, ckeys) and np.array_equal(order, cids)
     assert nodes.tobytes() == cn.tobytes()
-    del cn, cids, ckeys, nodes, order, keys
+    qn, grid = sc.bvh_export_compact()
+    cq, cgrid = oracle.bvh_compact(cn)
+    assert np.array_equal(bits(grid), bits(cgrid)) and qn.tobytes() == cq.tobytes()
+    del cn, cids, ckeys, nodes, order, keys, qn, cq
     o, d, _ = ray_batch("box", lambda xy: oracle.camera_rays(sd.ptr, xy), n_cam_side=96, n_random=30000)
     g = sc.trace_batch(o, d)
     c = oracle.trace_batch(sd.ptr, o, d, use_bvh=1)

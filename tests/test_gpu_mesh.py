@@ -21,6 +21,9 @@ def test_lbvh_build_bit_exact(n, lib, oracle):
     assert np.array_equal(keys, ckeys), "Morton keys / radix sort"
     assert np.array_equal(order, cids), "sorted primitive order"
     assert nodes.tobytes() == cn.tobytes(), "hierarchy + boxes"
+    qn, grid = sc.bvh_export_compact()   # the 32-byte nodes the traversal kernels read
+    cq, cgrid = oracle.bvh_compact(cn)
+    assert np.array_equal(bits(grid), bits(cgrid)) and qn.tobytes() == cq.tobytes(), "quantised traversal nodes"
     sc.close()
 
 

@@ -77,3 +77,29 @@ def test_mesh_render_bvh_equals_brute_force(lib, oracle):
     a = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 0)
     b = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 1)
     assert np.array_equal(a["sum"], b["sum"]) and a["rays"] == b["rays"]
+
+
+@pytest.mark.parametrize("n", [2, 37, 5000, 60000])
+def test_quantised_traversal_nodes_contain_the_float_boxes(n, lib, oracle):
+    """The 32-byte nodes the traversal kernels read (16-bit grid over the root box): every quantised child box contains
+    the float box of the 64-byte node with at least half a grid cell to spare on every side, is at most 3 cells larger, and carries the same child ids — so the traversal can visit a
+    node too many, never one too few."""
+    sd = capi.SceneDescription(f"mesh:{n}")
+    nodes, ids, keys = oracle.bvh_build(sd.triangles())
+    q, grid = oracle.bvh_compact(nodes)
+    lo, scale = grid[:3].astype(np.float64), grid[3:].astype(np.float64)
+    assert np.array_equal(q[:, 6], nodes["left"]) and np.array_equal(q[:, 7], nodes["right"])
+
+    def halves(w):
+        return (w & 0xFFFF).astype(np.float64), (w >> 16).astype(np.float64)
+
+    w = [halves(q[:, k]) for k in range(6)]
+    for child, (name_lo, name_hi) in enumerate([("lo0", "hi0"), ("lo1", "hi1")]):
+        b = 3 * child
+        qlo = np.stack([w[b][0], w[b][1], w[b + 1][0]], 1)
+        qhi = np.stack([w[b + 1][1], w[b + 2][0], w[b + 2][1]], 1)
+        glo = (nodes[name_lo].astype(np.float64) - lo) * scale * 65536.0 + 4.0   # float boxes in units of grid cells
+        ghi = (nodes[name_hi].astype(np.float64) - lo) * scale * 65536.0 + 4.0
+        assert (qlo <= glo - 0.5).all() and (glo - qlo <= 3).all()
+        assert (qhi >= ghi + 0.5).all() and (qhi - ghi <= 3).all()
+        assert (qlo >= 1).all() and (qhi <= 65534).all()                         # the root box leaves room for the rounding

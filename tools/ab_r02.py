@@ -9,9 +9,11 @@ VARIANTS = {
     "base": [],
     "nofast": ["IPT_FAST_SECONDARY=0"],
     "u24": ["IPT_U01_BITS=24"],
-    "r7": ["IPT_PHILOX_ROUNDS=7"],
-    "r7b4": ["IPT_PHILOX_ROUNDS=7", "IPT_SHADE_FUSED_MIN_BLOCKS=4", "IPT_SHADE_NEXT_MIN_BLOCKS=4"],
-    "nearr1": ["IPT_FAST_SECONDARY=0", "IPT_U01_BITS=24"],
+    "r10": ["IPT_PHILOX_ROUNDS=10"],
+    "b4": ["IPT_SHADE_FUSED_MIN_BLOCKS=4", "IPT_SHADE_NEXT_MIN_BLOCKS=4"],
+    "nearr1": ["IPT_FAST_SECONDARY=0", "IPT_U01_BITS=24", "IPT_PHILOX_ROUNDS=10", "IPT_BVH_WIDE_NODES=1", "IPT_LIGHT_TWO_QUEUES=0"],
+    "wide": ["IPT_BVH_WIDE_NODES=1"],      # mesh traversal over the 64-byte float nodes
+    "oneq": ["IPT_LIGHT_TWO_QUEUES=0"],    # many-light scenes: a single park queue at the non-last depths
 }
 if __name__ == "__main__":
     what = sys.argv[1]
@@ -20,13 +22,25 @@ if __name__ == "__main__":
         from ipt_b200 import build
         for n in names:
             print(n, build.build_variant(n, VARIANTS[n]), flush=True)
+    elif what == "configs":  # tools/run_configs.py per variant: python tools/ab_r02.py configs base,wide c3,c3_tree
+        for rep in range(2):
+            for n in names:
+                env = dict(os.environ, IPT_B200_LIB=f"ipt_b200/lib/variants/{n}.so")
+                r = subprocess.run([sys.executable, "tools/run_configs.py", sys.argv[3]], env=env, capture_output=True, text=True)
+                for l in r.stdout.strip().splitlines():
+                    try:
+                        d = json.loads(l)
+                        print(f"{n:8s} {d['config']:8s} {d['mpaths_per_s']:8.1f} Mpaths/s {d['mrays_per_s']:9.1f} Mrays/s  extend {d['ms_extend']:8.2f} shade {d['ms_shade']:8.2f} ms  "
+                              f"nodes/ray {d['bvh_nodes_per_ray']:.2f} tris/ray {d['tris_per_ray']:.2f} lnodes/ray {d.get('light_nodes_per_ray', 0):.2f} lights/ray {d.get('lights_per_ray', 0):.2f} mean {d['image_mean']:.6f}", flush=True)
+                    except Exception:
+                        print(n, "?", l[:300], r.stderr[-300:], flush=True)
     else:
         workloads = sys.argv[3].split(",") if len(sys.argv) > 3 else ["c2"]
         for rep in range(2):
             for n in names:
                 for w in workloads:
                     env = dict(os.environ, IPT_B200_LIB=f"ipt_b200/lib/variants/{n}.so")
-                    r = subprocess.run([sys.executable, "bench.py", "--workload", w, "--steps", "12", "--warmup", "3", "--no-cpu-baseline", "--e2e-steps", "1"],
+                    r = subprocess.run([sys.executable, "bench.py", "--workload", w, "--steps", "12", "--warmup", "3", "--no-cpu-baseline", "--e2e-steps", "1", "--no-c4"],
                                        env=env, capture_output=True, text=True)
                     try:
                         d = json.loads(r.stdout.strip().splitlines()[-1])

@@ -5,17 +5,9 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -s > gpurun_out/pytest2.log 2>&1; tail -3 gpurun_out/pytest2.log
 grep -E "IMAGE_STATS|FAILED|^E  " gpurun_out/pytest2.log | cut -c1-420 | head -60
 python bench.py --steps 24 --warmup 3 --with-c4 --c4-steps 3 > gpurun_out/bench2.json 2> gpurun_out/bench2.err; tail -c 1500 gpurun_out/bench2.json; tail -5 gpurun_out/bench2.err
-for v in main r7; do
-  if [ $v = main ]; then unset IPT_B200_LIB; else export IPT_B200_LIB=ipt_b200/lib/variants/$v.so; fi
-  python tools/run_configs.py c2,c1,c5_100,c5 2>&1 | python -c "
-import sys, json
-for l in sys.stdin:
-    try: d = json.loads(l)
-    except Exception: print(l[:300]); continue
-    print('$v', d['config'], round(d['mpaths_per_s'], 1), 'Mpaths/s shade ms', round(d['ms_shade'], 2), 'light nodes/ray', round(d.get('light_nodes_per_ray', -1), 2), 'lights/ray', round(d.get('lights_per_ray', -1), 2))
-"
-done
-unset IPT_B200_LIB
+python tools/ab_r02.py configs base,wide c3,c3_tree > gpurun_out/ab2_mesh.log 2>&1; cat gpurun_out/ab2_mesh.log
+python tools/ab_r02.py configs base,oneq c5_100,c5 > gpurun_out/ab2_lights.log 2>&1; cat gpurun_out/ab2_lights.log
+python tools/ab_r02.py run base,r10,nearr1 c2 > gpurun_out/ab2_c2.log 2>&1; cat gpurun_out/ab2_c2.log
 python tools/run_configs.py c1,c2,c3,c3_tree,c5_100,c5 > gpurun_out/configs2.jsonl 2>&1
 # ncu: launch list with DRAM bytes, then the two dominant launches in full
 python tools/profile_run.py cornell 1024 1024 2 > gpurun_out/plain.log 2>&1 && \
