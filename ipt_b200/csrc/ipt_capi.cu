@@ -63,6 +63,10 @@ struct Workspace {
     float* pathval = nullptr;
     size_t ray_cap = 0, hit_cap = 0, path_cap = 0;
     bool two_hit_sets = false;
+    // the batch the last render settled on for a (requested batch, queue widths, budget) combination: cudaMemGetInfo takes
+    // milliseconds on a 180 GB device, so the free-memory clamp is only re-evaluated when the question changes
+    uint64_t choice_key[5] = {0, 0, 0, 0, 0};
+    uint64_t choice_batch = 0;
 };
 
 // grow-only device scratch of the output stage (ipt_output.cuh): cudaMalloc/cudaFree per call would cost more than the
@@ -1134,15 +1138,20 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     // batch is halved again whenever the allocation itself fails.
     uint64_t budget = 24ull << 30;
     if (const char* e = std::getenv("IPT_QUEUE_BUDGET_GB")) { double gb = std::atof(e); if (gb > 0) budget = (uint64_t)(gb * (double)(1ull << 30)); }
-    {
+    const uint64_t choice_key[5] = {batch, max_queued_w, max_hit_w, budget, fuse_next ? 1ull : 0ull};
+    if (s->ws.choice_batch && std::memcmp(choice_key, s->ws.choice_key, sizeof choice_key) == 0 &&
+        s->ws.ray_cap >= s->ws.choice_batch * max_queued_w && s->ws.hit_cap >= s->ws.choice_batch * max_hit_w && s->ws.path_cap >= s->ws.choice_batch) {
+        batch = s->ws.choice_batch; // same question as last time and the workspace it led to is still allocated
+    } else {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             const Workspace& w0 = s->ws;
             uint64_t held = w0.path_cap ? workspace_bytes(w0.ray_cap, w0.hit_cap, w0.path_cap, w0.two_hit_sets) : 0;
             budget = std::min<uint64_t>(budget, (uint64_t)((double)(free_b + held) * 0.8));
         } else cudaGetLastError();
+        while (batch > 1024 && workspace_bytes(batch * max_queued_w, batch * max_hit_w, batch, fuse_next) > budget) batch >>= 1;
     }
-    while (batch > 1024 && workspace_bytes(batch * max_queued_w, batch * max_hit_w, batch, fuse_next) > budget) batch >>= 1;
+    const uint64_t batch_unclamped = batch;
     batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(total_paths, 1)));
     if ((uint64_t)tw * th + batch > 0xFFFFFFFFull) return fail(IPT_ERR_UNSUPPORTED, "tile too large: tile pixels + batch must stay below 2^32");
     for (;;) {
@@ -1150,6 +1159,10 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
         if (rc == IPT_OK) break;
         if (rc != IPT_ERR_OVERFLOW || batch <= 1024) return rc;
         batch >>= 1; // another tenant (torch, NCCL) took the memory between the query and the allocation
+    }
+    if (batch == std::min<uint64_t>(batch_unclamped, std::max<uint64_t>(total_paths, 1)) && batch_unclamped <= total_paths) {
+        std::memcpy(s->ws.choice_key, choice_key, sizeof choice_key);
+        s->ws.choice_batch = batch_unclamped;
     }
 
     RenderCtx C;
@@ -1159,6 +1172,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     C.hit_a[1] = fuse_next ? s->ws.hit_a2 : s->ws.hit_a; C.hit_b[1] = fuse_next ? s->ws.hit_b2 : s->ws.hit_b;
     C.cnt = s->d_cnt; C.fetch = s->d_cnt + (2 * IPT_MAX_DEPTH + 2); C.stats = s->d_stats;
     C.sum = plane->sum; C.sumsq = plane->sumsq; C.count = plane->count;
+    C.ray_cap = (uint32_t)std::min<size_t>(s->ws.ray_cap, 0xFFFFFFFFull); C.hit_cap = (uint32_t)std::min<size_t>(s->ws.hit_cap, 0xFFFFFFFFull);
     C.width = p->width; C.height = p->height;
     C.tile_x0 = tx0; C.tile_y0 = ty0; C.tile_w = tw; C.tile_h = th; C.tile_pixels = tw * th;
     C.pass_begin = p->pass_begin;
@@ -1282,6 +1296,13 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaGetLastError());
 
+#ifdef IPT_DEBUG_BOUNDS
+    {
+        unsigned long long over = 0;
+        CUDA_TRY(cudaMemcpy(&over, s->d_stats + ST_OVERFLOW, sizeof over, cudaMemcpyDeviceToHost));
+        if (over) return fail(IPT_ERR_OVERFLOW, std::to_string(over) + " queue append(s) beyond the allocated capacity (IPT_DEBUG_BOUNDS build)");
+    }
+#endif
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         unsigned long long h[ST_COUNT];

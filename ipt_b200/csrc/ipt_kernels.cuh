@@ -31,6 +31,15 @@
 #define IPT_EXTEND_MIN_BLOCKS 3
 #endif
 #include <cstdio>
+// -DIPT_DEBUG_BOUNDS: every queue append checks its slot against the capacity the host allocated and every park-queue
+// write against IPT_PARK; violations are counted (ST_OVERFLOW) instead of written, and ipt_render returns IPT_ERR_OVERFLOW.
+// compute-sanitizer is not available on this pool, so this build (tools/ab_r02.py variant "bounds") is what checks that the
+// worst-case queue sizing really is the worst case.
+#ifdef IPT_DEBUG_BOUNDS
+#define IPT_BOUNDS_OK(index, capacity, stats) ((index) < (capacity) ? true : (atomicAdd(&(stats)[ST_OVERFLOW], 1ull), false))
+#else
+#define IPT_BOUNDS_OK(index, capacity, stats) true
+#endif
 #ifndef IPT_LIGHT_TWO_QUEUES
 #define IPT_LIGHT_TWO_QUEUES 1 // 0: one park queue for every child of a many-light scene (tuning A/B only)
 #endif
@@ -43,7 +52,7 @@ namespace iptd {
 enum LightQuery { LQ_PDF = 0, LQ_NEAREST = 1, LQ_BOTH = 2 };
 
 enum StatSlot {
-    ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED, ST_FUSED, ST_LIGHT_NODES,
+    ST_SURFACE = 0, ST_LIGHT, ST_MISS, ST_FAILED, ST_PRUNED, ST_DROPPED, ST_NODES, ST_TRIS, ST_LIGHTS, ST_PATHS, ST_QUEUED, ST_FUSED, ST_LIGHT_NODES, ST_OVERFLOW,
     ST_RAYS_AT_DEPTH = 16, // + depth
     ST_COUNT = 16 + IPT_MAX_DEPTH
 };
@@ -69,6 +78,7 @@ struct RenderCtx {
     uint32_t pass_begin;
     unsigned long long g0; // first global path index of the batch
     uint32_t batch;        // paths in this batch
+    uint32_t ray_cap, hit_cap; // allocated records per ray queue / hit set (checked by -DIPT_DEBUG_BOUNDS builds)
     uint32_t slot_bits, slot_mask;
     uint32_t depth_max;
     uint32_t schedule[IPT_MAX_DEPTH];
@@ -414,8 +424,10 @@ __global__ void __launch_bounds__(256, IPT_EXTEND_MIN_BLOCKS) k_extend(const __g
                     f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), oc.surf.t);
                     uint32_t iprim = oc.surf.tri_pos != IPT_NO_HIT ? S.n_prims + oc.surf.tri_pos : oc.surf.prim;
                     float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
-                    C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, ro.w);
-                    C.hit_b[depth & 1][j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+                    if (IPT_BOUNDS_OK(j, C.hit_cap, C.stats)) {
+                        C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, ro.w);
+                        C.hit_b[depth & 1][j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+                    }
                 }
             }
         }
@@ -547,8 +559,10 @@ __device__ __forceinline__ void extend_parked(const DevScene& S, const RenderCtx
             uint32_t j = basepos + __popc(ballot & ((1u << lane) - 1u));
             f3 p = xpoint(o, d, oc.surf.t);
             float2 oct = oct_encode(d);
-            C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, wr);
-            C.hit_b[depth & 1][j] = make_uint4(ctag, oc.surf.prim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+            if (IPT_BOUNDS_OK(j, C.hit_cap, C.stats)) {
+                C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, wr);
+                C.hit_b[depth & 1][j] = make_uint4(ctag, oc.surf.prim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+            }
         }
     }
 }
@@ -661,6 +675,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                 if (pb) {
                     if (to_lights) {
                         uint32_t k = qn + __popc(pb & ((1u << lane) - 1u));
+                        if (!IPT_BOUNDS_OK(k, (uint32_t)IPT_PARK, C.stats)) k = IPT_PARK - 1;
                         dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
                         dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
                         dq[6 * IPT_PARK + k] = wgt; dq[7 * IPT_PARK + k] = child_sv; dq[8 * IPT_PARK + k] = __uint_as_float(ctag);
@@ -678,6 +693,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     if (pb2) {
                         if (plain) {
                             uint32_t k = qn2 + __popc(pb2 & ((1u << lane) - 1u));
+                            if (!IPT_BOUNDS_OK(k, (uint32_t)IPT_PARK, C.stats)) k = IPT_PARK - 1;
                             dq2[0 * IPT_PARK + k] = pos.x; dq2[1 * IPT_PARK + k] = pos.y; dq2[2 * IPT_PARK + k] = pos.z;
                             dq2[3 * IPT_PARK + k] = w.x; dq2[4 * IPT_PARK + k] = w.y; dq2[5 * IPT_PARK + k] = w.z;
                             dq2[6 * IPT_PARK + k] = wgt; dq2[7 * IPT_PARK + k] = child_sv; dq2[8 * IPT_PARK + k] = __uint_as_float(ctag);
@@ -709,6 +725,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                     if (pbb) {
                         if (parkb) {
                             uint32_t k = qn + __popc(pbb & ((1u << lane) - 1u));
+                            if (!IPT_BOUNDS_OK(k, (uint32_t)IPT_PARK, C.stats)) k = IPT_PARK - 1;
                             dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
                             dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
                             dq[6 * IPT_PARK + k] = wgt; dq[7 * IPT_PARK + k] = child_sv;
@@ -743,6 +760,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                 if (pb) {
                     if (park) {
                         uint32_t k = qn + __popc(pb & ((1u << lane) - 1u));
+                        if (!IPT_BOUNDS_OK(k, (uint32_t)IPT_PARK, C.stats)) k = IPT_PARK - 1;
                         dq[0 * IPT_PARK + k] = pos.x; dq[1 * IPT_PARK + k] = pos.y; dq[2 * IPT_PARK + k] = pos.z;
                         dq[3 * IPT_PARK + k] = w.x; dq[4 * IPT_PARK + k] = w.y; dq[5 * IPT_PARK + k] = w.z;
                         dq[6 * IPT_PARK + k] = ldist; dq[7 * IPT_PARK + k] = contrib; dq[8 * IPT_PARK + k] = __uint_as_float(tag & C.slot_mask);
@@ -766,9 +784,11 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
                 if (emit) {
                     uint32_t j = basepos + __popc(ballot & ((1u << lane) - 1u));
                     uint32_t ctag = (tag & C.slot_mask) | (C.slot_bits == 32 ? 0u : (child << C.slot_bits));
-                    C.ray_o[j] = make_float4(pos.x, pos.y, pos.z, wgt);
-                    C.ray_d[j] = make_float4(w.x, w.y, w.z, __uint_as_float(ctag));
-                    C.ray_x[j] = child_sv;
+                    if (IPT_BOUNDS_OK(j, C.ray_cap, C.stats)) {
+                        C.ray_o[j] = make_float4(pos.x, pos.y, pos.z, wgt);
+                        C.ray_d[j] = make_float4(w.x, w.y, w.z, __uint_as_float(ctag));
+                        C.ray_x[j] = child_sv;
+                    }
                 }
             }
         }

@@ -46,8 +46,10 @@ __device__ __forceinline__ float slab(float lox, float loy, float loz, float hix
 // A ray is mapped once: entry / exit distances of a slab at grid coordinate g are  t = g * inv + c  with inv = 1 / d' and
 // c = -o' * inv. t is the world-space ray parameter (GridMap), so it compares directly with the best hit distance. The
 // quantised boxes are a full grid cell (1.5e-5) larger than the float boxes on every side; the float error of the mapped
-// ray and of the fused multiply-add is below 1e-6 grid units, so the test stays conservative. An axis with d == 0
-// yields NaN and drops out of the fminf / fmaxf chain (the axis then does not constrain: conservative).
+// ray and of the fused multiply-add is below 1e-6 grid units, so the test stays conservative. 1 / d' is clamped to +-1e37:
+// with an infinite reciprocal (a direction component that is exactly 0, which sampled directions do hit at a 2^-23 rate)
+// g * inf - o' * inf would be NaN for every box, the axis would stop culling and the ray would walk the whole tree; with
+// the clamp a ray outside the slab still gets two huge distances of the same sign and is culled.
 #ifndef IPT_BVH_WIDE_NODES
 #define IPT_BVH_WIDE_NODES 0 // 1: traverse the 64-byte float nodes instead (tuning A/B only)
 #endif
@@ -63,7 +65,8 @@ __device__ __forceinline__ GridRay grid_ray(const GridMap& G, f3 o, f3 d) {
 #endif
     float ox = __fmaf_rn(__fsub_rn(o.x, G.lo[0]), G.scale[0], IPT_GRID_BASE), oy = __fmaf_rn(__fsub_rn(o.y, G.lo[1]), G.scale[1], IPT_GRID_BASE),
           oz = __fmaf_rn(__fsub_rn(o.z, G.lo[2]), G.scale[2], IPT_GRID_BASE);
-    r.inv = mk3(1.0f / (d.x * G.scale[0]), 1.0f / (d.y * G.scale[1]), 1.0f / (d.z * G.scale[2]));
+    float dx = d.x * G.scale[0], dy = d.y * G.scale[1], dz = d.z * G.scale[2];
+    r.inv = mk3(copysignf(fminf(fabsf(1.0f / dx), 1e37f), dx), copysignf(fminf(fabsf(1.0f / dy), 1e37f), dy), copysignf(fminf(fabsf(1.0f / dz), 1e37f), dz));
     r.c = mk3(-ox * r.inv.x, -oy * r.inv.y, -oz * r.inv.z);
     return r;
 }
@@ -421,8 +424,10 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                     uint32_t j = basepos + __popc(ballot & lt_mask);
                     f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), t);
                     float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
-                    C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, ro.w);
-                    C.hit_b[depth & 1][j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+                    if (IPT_BOUNDS_OK(j, C.hit_cap, C.stats)) {
+                        C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, ro.w);
+                        C.hit_b[depth & 1][j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
+                    }
                 }
             }
         }

@@ -430,7 +430,7 @@ struct CachedContext {
     bool alive() const { return !geometry.expired() && !lighting.expired() && !camera.expired(); }
 };
 std::mutex g_cache_mu;
-std::map<std::tuple<const void*, const void*, const void*, int>, CachedContext> g_cache;
+std::map<std::tuple<const void*, const void*, const void*, int, size_t>, CachedContext> g_cache;
 
 #ifdef IPT_B200_REFERENCE_CLASSES
 // The reference's data-free geometries: the class IS the scene (its primitives are literals inside traceRay).
@@ -467,7 +467,9 @@ bool export_camera(const Camera* c, SceneBuilder& b) {
     return false;
 }
 
-std::shared_ptr<DeviceContext> context_for(const Scene& scene, int device) {
+// `replica`: which of the slots naming the SAME device this is (render_sample(scene, plane, params, {0, 0}) runs two host
+// threads on one GPU): an ipt_scene owns one stream and one workspace, so concurrent renders need one scene replica each.
+std::shared_ptr<DeviceContext> context_for(const Scene& scene, int device, size_t replica = 0) {
     SceneBuilder b;
     const DeviceExportable* l = dynamic_cast<const DeviceExportable*>(scene.lighting.get());
     if (!l || !export_geometry(scene.geometry.get(), b) || !export_camera(scene.camera.get(), b))
@@ -476,7 +478,7 @@ std::shared_ptr<DeviceContext> context_for(const Scene& scene, int device) {
                     "for geometry and camera in a build against the reference's headers, the reference's own data-free Geometry classes / "
                     "SimpleCamera; other classes hide their data and there is no CPU fallback");
     std::lock_guard<std::mutex> lock(g_cache_mu);
-    auto key = std::make_tuple((const void*)scene.geometry.get(), (const void*)scene.lighting.get(), (const void*)scene.camera.get(), device);
+    auto key = std::make_tuple((const void*)scene.geometry.get(), (const void*)scene.lighting.get(), (const void*)scene.camera.get(), device, replica);
     for (auto e = g_cache.begin(); e != g_cache.end();) e = e->second.alive() ? std::next(e) : g_cache.erase(e); // drop dead scenes
     const DeviceExportable* ge = dynamic_cast<const DeviceExportable*>(scene.geometry.get());
     const uint64_t grev = ge ? ge->revision() : 0, lrev = l->revision();
@@ -556,7 +558,8 @@ ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const i
     p.plane_mode = dp ? dp->plane_mode : gp ? (uint32_t)IPT_PLANE_GRID : (uint32_t)IPT_PLANE_LINEAR;
     const size_t world = devices.size();
     std::vector<std::shared_ptr<DeviceContext>> ctx(world);
-    for (size_t r = 0; r < world; ++r) ctx[r] = context_for(scene, devices[r]); // scene replicas (cached per device)
+    for (size_t r = 0; r < world; ++r) // scene replicas (cached per device; slots that name the same device get one each)
+        ctx[r] = context_for(scene, devices[r], (size_t)std::count(devices.begin(), devices.begin() + r, devices[r]));
     // accumulators: device 0 renders into the caller's DevicePlane (or a scratch plane), the others into scratch planes
     std::vector<PlaneHandle> scratch(world);
     std::vector<ipt_plane*> plane(world, nullptr);

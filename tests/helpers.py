@@ -44,3 +44,39 @@ def ray_batch(scene_name, camera_rays_fn, n_cam_side=96, n_random=20000, seed=7)
 
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _oracle_render_worker(args):
+    scene, kw, seed, pass_begin, pass_count, use_bvh = args
+    import oracle_lib
+    from ipt_b200 import capi
+
+    sd = capi.SceneDescription(scene)
+    p = capi.default_params(pass_begin=pass_begin, pass_count=pass_count, seed=seed, **kw)
+    o = oracle_lib.load_oracle().render(sd.ptr, p, oracle_lib.RNG_PHILOX, use_bvh)
+    return o["sum"], o["sumsq"], o["counters"], o["rays"]
+
+
+def oracle_render_parallel(scene, passes, seed, use_bvh=0, workers=None, **kw):
+    """The oracle's Philox-mode render (test infrastructure: the CPU checker) of `passes` passes, split into contiguous pass
+    ranges over forked single-threaded processes (Philox counters are keyed by (pixel, pass, node), so the ranges are
+    disjoint streams and the merged accumulators equal a single render). Returns dict(sum, sumsq, count, rays)."""
+    import multiprocessing as mp
+    import os
+
+    workers = max(1, min(workers or (os.cpu_count() or 1), passes))
+    base, extra = divmod(passes, workers)
+    jobs, begin = [], 0
+    for r in range(workers):
+        n = base + (1 if r < extra else 0)
+        jobs.append((scene, kw, seed, begin, n, use_bvh))
+        begin += n
+    with mp.get_context("fork").Pool(workers) as pool:
+        res = pool.map(_oracle_render_worker, jobs)
+    return dict(sum=sum(r[0] for r in res), sumsq=sum(r[1] for r in res), count=sum(r[2] for r in res), rays=sum(r[3] for r in res))
+
+
+def block_sums(a, block):
+    """Sums of block x block cells (frames whose sides are multiples of `block`)."""
+    H, W = a.shape
+    return a.reshape(H // block, block, W // block, block).sum((1, 3))

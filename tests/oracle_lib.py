@@ -227,6 +227,17 @@ class Oracle(_OutputStage):
         self.lib.ipt_oracle_bvh_compact(nodes.ctypes.data_as(C.c_void_p), C.c_uint64(len(nodes)), _p(out, u32p), _p(grid, f32p))
         return out, grid
 
+    def bvh_trace_counts(self, triangles, o, d, compact):
+        """Closest triangle per ray over the float nodes (compact=0) or the quantised nodes (compact=1), with the node visits and
+        triangle tests it took: dict(prim, t, nodes, tris)."""
+        t = _f32(triangles).reshape(-1, 9); o, d = _f32(o).reshape(-1, 3), _f32(d).reshape(-1, 3)
+        n = o.shape[0]
+        prim = np.empty(n, np.uint32); tt = np.empty(n, np.float32); nodes = np.empty(n, np.uint32); tris = np.empty(n, np.uint32)
+        rc = self.lib.ipt_oracle_bvh_trace_counts(_p(t, f32p), C.c_uint64(t.shape[0]), _p(o, f32p), _p(d, f32p), C.c_uint64(n), int(compact),
+                                                  _p(prim, u32p), _p(tt, f32p), _p(nodes, u32p), _p(tris, u32p))
+        assert rc == 0
+        return dict(prim=prim, t=tt, nodes=nodes, tris=tris)
+
     def philox_rounds(self, rounds, c, k):
         out = (C.c_uint32 * 4)()
         self.lib.ipt_oracle_philox_rounds(rounds, *[C.c_uint32(v) for v in c], *[C.c_uint32(v) for v in k], out)

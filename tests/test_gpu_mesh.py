@@ -77,30 +77,67 @@ def test_mesh_render_matches_oracle(lib, oracle):
     sc.close()
 
 
-@pytest.mark.parametrize("scene,size,depth,schedule,cpu_passes,gpu_passes", [
-    ("mesh:1000000", 64, 8, [1] * 8, 768, 16384),    # BASELINE configs[2]: depth 8, one child per hit
-    ("mesh:100000", 32, 4, [16, 8, 4, 2], 192, 4096),  # the reference's own tree on a mesh
+def test_c3_one_million_triangles_depth_8_with_common_random_numbers(lib, oracle):
+    """BASELINE configs[2] (1 M triangles, depth 8, one child per hit) with the SAME Philox numbers on both sides: the mesh
+    path traces every depth with the reference's exact arithmetic, so a pixel differs from the oracle only where an ulp of
+    the sampled direction (CUDA vs glibc sin/cos) flips a hit decision somewhere along one of its paths. The large majority
+    of the pixels is identical to float rounding, the rest is unbiased, and the ray counts agree per depth."""
+    sd = capi.SceneDescription("mesh:1000000")
+    sc = capi.Scene(sd)
+    p = capi.default_params(width=96, height=96, pass_count=16, depth_max=8, schedule=[1] * 8, flags=capi.FLAG_KEEP_ZERO_WEIGHT)
+    s, q, cnt, st = sc.render_host(p)
+    o = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 1)
+    assert np.array_equal(cnt.astype(np.uint64), o["counters"]) and st.paths == 96 * 96 * 16
+    scale = max(o["sum"].max(), 1e-12)
+    diff = s - o["sum"]
+    same = np.abs(diff) / scale <= 1e-5
+    lit = o["sum"] > 0
+    print(f"C3_CRN identical={same.mean():.5f} identical_lit={same[lit].mean():.5f} lit={lit.mean():.4f} rays {st.rays} vs {o['rays']}")
+    assert same.mean() > 0.97 and same[lit].mean() > 0.9
+    d = diff[~same]
+    if d.size > 20:
+        assert abs(d.mean()) < 5 * d.std() / np.sqrt(d.size)
+    assert st.rays_at_depth[0] == o["rays_at_depth"][0] == 96 * 96 * 16
+    for k in range(8):
+        assert abs(int(st.rays_at_depth[k]) - int(o["rays_at_depth"][k])) <= 5e-3 * o["rays_at_depth"][k] + 8
+    sc.close()
+
+
+@pytest.mark.parametrize("scene,size,depth,schedule,cpu_passes,gpu_passes,block", [
+    # BASELINE configs[2]: depth 8, one child per hit. A path reaches the light with probability ~1e-3, so a pixel sees a
+    # handful of non-zero samples even in thousands of passes and its mean is far from Gaussian: the scores are taken on
+    # 16x16-pixel cells (hundreds of non-zero samples each on the CPU side). The oracle traces this mesh at 0.2 Mrays/s per
+    # core, so this is a sanity check of modest power; the sharp comparison is the common-random-number test above
+    ("mesh:1000000", 64, 8, [1] * 8, 1024, 65536, 16),
+    # the reference's own tree on a mesh: splitting 16/8/4/2 makes every pixel well behaved
+    ("mesh:100000", 32, 4, [16, 8, 4, 2], 256, 4096, 1),
 ])
-def test_mesh_image_z_test_against_oracle(scene, size, depth, schedule, cpu_passes, gpu_passes, lib, oracle):
+def test_mesh_image_z_test_against_oracle(scene, size, depth, schedule, cpu_passes, gpu_passes, block, lib, oracle):
     """Converged-image parity of the mesh path (the reference has no mesh geometry, SURVEY S1: the oracle's GeometryMesh over
-    the CPU LBVH is the checker). INDEPENDENT random numbers on the two sides (different Philox keys): per-pixel z-test of
-    the means, bias detector, block relRMSE — SURVEY 8d's procedure, same assertions as test_converged_image_matches_reference."""
+    the CPU LBVH is the checker). INDEPENDENT random numbers on the two sides (different Philox keys): z-test of the means
+    per cell (pixel, or block of pixels where single pixels are too sparse), bias detector, image mean. The oracle runs as
+    forked processes over disjoint pass ranges. Tolerances: >= 99.7 % of the cells |z| < 3 up to three standard errors of
+    that fraction, |mean z| below 3 / sqrt(cells) (three standard errors of the mean of N(0,1) scores) and never above
+    0.1 where there are enough cells for that, image mean within 3 sigma of the two estimates + 0.2 %, and the relative
+    RMSE of 8x8 block means below 1 % + 1.5x the RMSE the two sides' own variances predict (the CPU side cannot afford the
+    passes that would push its own noise below 1 %)."""
+    from helpers import block_sums, oracle_render_parallel
     from test_gpu_golden import image_stats
+    from test_oracle_golden import same_coverage
 
     sd = capi.SceneDescription(scene)
     sc = capi.Scene(sd)
     kw = dict(width=size, height=size, depth_max=depth, schedule=schedule)
-    o = oracle.render(sd.ptr, capi.default_params(pass_count=cpu_passes, seed=1234, **kw), oracle_lib.RNG_PHILOX, 1)
+    o = oracle_render_parallel(scene, cpu_passes, seed=1234, use_bvh=1, **kw)
     s, q, cnt, st = sc.render_host(capi.default_params(pass_count=gpu_passes, seed=98765, **kw))
-    g = dict(sum=o["sum"], sumsq=o["sumsq"], count=o["counters"])
-    from test_oracle_golden import same_coverage
-
-    assert same_coverage(cnt, gpu_passes, g["count"], cpu_passes)
-    r = image_stats(s, q, cnt, g, block=8 if size >= 64 else 4)
-    print(f"IMAGE_STATS {scene} depth {depth} " + " ".join(f"{k}={v:.5g}" for k, v in r.items()))
+    assert same_coverage(cnt, gpu_passes, o["count"], cpu_passes)
+    g = dict(sum=block_sums(o["sum"], block), sumsq=block_sums(o["sumsq"], block), count=block_sums(o["count"], block))
+    r = image_stats(block_sums(s.astype(np.float64), block), block_sums(q.astype(np.float64), block), block_sums(cnt.astype(np.uint64), block), g,
+                    block=max(1, 8 // block))
+    print(f"IMAGE_STATS {scene} depth {depth} cells of {block}x{block} " + " ".join(f"{k}={v:.5g}" for k, v in r.items()))
     assert r["frac3"] >= r["frac3_floor"], r
-    assert abs(r["mean_z"]) < 0.1, r
-    assert r["block_rel_rmse"] < 0.01, r
-    assert abs(r["mean_rel"]) < 0.005, r
-    assert abs(st.rays / st.paths - o["rays"] / o["counters"].sum()) < 0.01 * st.rays / st.paths
+    assert abs(r["mean_z"]) < max(0.1, 3.0 / np.sqrt(r["n_lit"])), r
+    assert abs(r["mean_rel"]) < 3 * r["mean_rel_sigma"] + 0.002, r
+    assert r["block_rel_rmse"] < 0.01 + 1.5 * r["block_noise_rel"], r
+    assert abs(st.rays / st.paths - o["rays"] / o["count"].sum()) < 0.01 * st.rays / st.paths
     sc.close()
