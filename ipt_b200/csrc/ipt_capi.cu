@@ -1286,7 +1286,8 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 continue;
             }
             int gs = std::max(1, std::min(s->grid_shade, cap_blocks));
-            TIMED(2, (k_shade<FUSE_NONE, false><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+            if (s->smallpt) TIMED(2, (k_shade<FUSE_NONE, true><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d))); // reference-order sampling (ipt_shading.cuh)
+            else TIMED(2, (k_shade<FUSE_NONE, false><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
         }
         TIMED(3, (k_accumulate<<<std::max(1, gg), IPT_BLOCK, 0, s->stream>>>(C)));
 #undef TIMED

@@ -634,8 +634,9 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             f3 din = mk3(0, 0, 0);
             if (SPEC != SPEC_LAMBERT_BOX && m.ddf == IPT_DDF_GLOSSY) din = oct_decode(__uint_as_float(b.z), __uint_as_float(b.w)); // only the glossy lobe needs it
             sdf = make_sdf(m, normal, din);
-            bn = make_basis(normal);
-            bl = (SPEC != SPEC_LAMBERT_BOX && m.ddf == IPT_DDF_GLOSSY) ? make_basis(sdf.refl) : bn;
+            // SmallPt scenes: the reference's own operation sequence for the rotation and the samples (ipt_shading.cuh)
+            bn = SMALLPT ? make_basis_exact(normal) : make_basis(normal);
+            bl = (SPEC != SPEC_LAMBERT_BOX && m.ddf == IPT_DDF_GLOSSY) ? (SMALLPT ? make_basis_exact(sdf.refl) : make_basis(sdf.refl)) : bn;
         }
         const float hit_k = pmul(pmul(thr, albedo), inv_n);
         for (uint32_t c = 0; c < n_children; ++c) {
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(256, FUSE == FUSE_LAST ? IPT_SHADE_FUSED_MIN_B
             uint32_t child = node * n_children + c;
             if (active) {
                 uint4 r = philox4x32(pixel, pass, child, depth + 1, C.keys);
-                w = mix_sample<IPT_SPEC_INLINE_LIGHTS(SPEC), IPT_SPEC_AREA_LIGHTS(SPEC), SPEC == SPEC_LAMBERT_BOX>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+                w = mix_sample<IPT_SPEC_INLINE_LIGHTS(SPEC), IPT_SPEC_AREA_LIGHTS(SPEC), SPEC == SPEC_LAMBERT_BOX, SMALLPT>(S, sdf, bn, bl, pos, u01(r.x), u01(r.y), u01(r.z), u01(r.w));
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f) {
 #ifdef IPT_DEBUG_PRINT
                     if (FUSE == FUSE_NONE && (C.flags & IPT_FLAG_DEBUG_PRINT)) printf("GPU shade d=%u child=%u u=(%.9g %.9g %.9g) FAILED\n", depth, child, u01(r.x), u01(r.y), u01(r.z));

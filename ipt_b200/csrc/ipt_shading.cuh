@@ -50,6 +50,49 @@ __device__ __forceinline__ f3 rotate(const Basis& b, f3 x) {
                pfma(b.c2.z, x.z, pfma(b.c1.z, x.y, pmul(b.c0.z, x.x))));
 }
 
+// ---- reference-order sampling (EXACT = true; the SmallPt scene) ---------------------------------------------------------
+// GeometrySmallPt intersects radius-1000 spheres with the unit-direction formula and eps = 1e-4 (GeometrySmallPt.cpp:17-22):
+// a direction whose length is off by 1e-7 moves the computed hit point 1e-5 off the sphere, which decides whether the NEXT
+// ray re-hits the wall it starts on (11 % of the rays of that scene do). The image therefore depends on the rounding errors
+// of the sampled directions' lengths — scaling every sampled direction by (1 - 1e-7) darkens it by 0.7 % — and those
+// errors are not zero-mean per hit: the columns of RotateDdf's float matrix are off by up to 1e-7 for a given normal. For
+// that scene the sampling code below follows the reference's operation sequence (glm::rotate, acos / sin / cos of the
+// angles, glm's mat3 * vec3, normalize) with IEEE operations; sin / cos / acos are evaluated in double and rounded, which
+// agrees with glibc's float functions (< 0.56 ulp) in all but a few per cent of the arguments, and then by one ulp.
+__device__ __forceinline__ float sin_r(float a) { return __double2float_rn(sin((double)a)); }
+__device__ __forceinline__ float cos_r(float a) { return __double2float_rn(cos((double)a)); }
+__device__ __forceinline__ float acos_r(float a) { return __double2float_rn(acos((double)a)); }
+// RotateDdf::RotateDdf (src/libddf/ddf_detail.h:72-85) over glm::rotate(identity, angle, axis) (glm/ext/matrix_transform.inl:18-46)
+__device__ __forceinline__ Basis make_basis_exact(f3 to) {
+    f3 z = mk3(0.0f, 0.0f, 1.0f);
+    f3 axis = xcross3(z, to);
+    if (lt_1e6(xlength3(axis))) axis = mk3(1.0f, 0.0f, 0.0f); // length(axis) < 1e-6 (double literal)
+    float cosinus = xdot3(z, to);
+    float a = acos_r(cosinus); // ddf_detail.h:76 calls the double acos
+    float c = cos_r(a), s = sin_r(a);
+    f3 ax = xnormalize3(axis);
+    f3 temp = xscale3(ax, xsub(1.0f, c));
+    Basis b;
+    b.c0 = mk3(xadd(c, xmul(temp.x, ax.x)), xadd(xmul(temp.x, ax.y), xmul(s, ax.z)), xsub(xmul(temp.x, ax.z), xmul(s, ax.y)));
+    b.c1 = mk3(xsub(xmul(temp.y, ax.x), xmul(s, ax.z)), xadd(c, xmul(temp.y, ax.y)), xadd(xmul(temp.y, ax.z), xmul(s, ax.x)));
+    b.c2 = mk3(xadd(xmul(temp.z, ax.x), xmul(s, ax.y)), xsub(xmul(temp.z, ax.y), xmul(s, ax.x)), xadd(c, xmul(temp.z, ax.z)));
+    return b;
+}
+// glm mat3 * vec3 (glm/detail/type_mat3x3.inl:468-474): (m[0][i] * v.x + m[1][i] * v.y) + m[2][i] * v.z
+__device__ __forceinline__ f3 rotate_exact(const Basis& b, f3 x) {
+    return mk3(xadd(xadd(xmul(b.c0.x, x.x), xmul(b.c1.x, x.y)), xmul(b.c2.x, x.z)), xadd(xadd(xmul(b.c0.y, x.x), xmul(b.c1.y, x.y)), xmul(b.c2.y, x.z)),
+               xadd(xadd(xmul(b.c0.z, x.x), xmul(b.c1.z, x.y)), xmul(b.c2.z, x.z)));
+}
+// CosineDdf::sample / the PowerCosine extension in their own frame (src/libddf/ddf.cpp:91-102): cos(alpha) = u1^(1/(n+1)),
+// alpha = acos(.), phi = 2 pi u2 (double product, rounded), (sin(alpha) cos(phi), sin(alpha) sin(phi), cos(alpha))
+__device__ __forceinline__ f3 lobe_sample_exact(bool lobe, float inv_np1, float u1, float u2) {
+    float zc = lobe ? powf(u1, inv_np1) : xsqrt(u1);
+    float alpha = acos_r(zc);
+    float phi = __double2float_rn(__dmul_rn(6.283185307179586, (double)u2));
+    float r = sin_r(alpha);
+    return mk3(xmul(r, cos_r(phi)), xmul(r, sin_r(phi)), zc);
+}
+
 // Base DDFs in their own frame. kind: 0 Spherical (ddf.cpp:58-72), 1 UpperHalf (:74-89), 2 Cosine (:91-108),
 // >=3 PowerCosine(kind) (extension, oracle/ref_driver.cpp).
 // z^n for a small non-negative integer n by square-and-multiply (the glossy lobe's exponent is an integer >= 3)
@@ -131,9 +174,15 @@ __device__ __forceinline__ float sdf_value(const Sdf& s, f3 w) {
 }
 // zero vector == failed sample. ul is the lobe-selection draw (ROLE_LOBE in the oracle).
 // bl: basis about the mirror direction (== bn for Lambert hits; built once per hit, not per child)
-template <bool LAMBERT = false>
+template <bool LAMBERT = false, bool EXACT = false>
 __device__ __forceinline__ f3 sdf_sample(const Sdf& s, const Basis& bn, const Basis& bl, float u1, float u2, float ul) {
     bool lobe = !LAMBERT && !(ul < s.wd);   // never for Lambert (wd = 1 > ul)
+    if (EXACT) { // reference-order arithmetic (see make_basis_exact)
+        f3 x = lobe_sample_exact(lobe, s.inv_np1, u1, u2);
+        f3 w = lobe ? rotate_exact(bl, x) : rotate_exact(bn, x);
+        bool below = !LAMBERT && s.ddf == IPT_DDF_GLOSSY && xdot3(s.normal, w) < 0.0f;
+        return below ? mk3(0, 0, 0) : w;
+    }
     float e = lobe ? s.inv_np1 : 0.5f;      // cos(alpha) = u1^(1/(n+1)); sqrt(u1) for the cosine DDF (ddf.cpp:94)
     float zc = exp2f(pmul(__log2f(u1), e)); // u1 = 0 -> 0
     float r = fsqrt(fmaxf(0.0f, pfma(-zc, zc, 1.0f)));
@@ -181,9 +230,18 @@ __device__ __forceinline__ float light_pdf_at(const DevLight& L, f3 pos, f3 hit)
 }
 
 // DdfFromLight::sample (src/lighting/lighting.cpp:50-59) over Light::sample (lighting.cpp:93-104, 172-207)
-template <bool AREA = false>
+template <bool AREA = false, bool EXACT = false>
 __device__ __forceinline__ f3 light_sample_dir(const DevLight& L, f3 pos, float u1, float u2) {
     f3 p, n;
+    if (EXACT && (AREA || L.kind <= IPT_LIGHT_AREA_TRIANGLE)) {
+        // AreaLight::sample + DdfFromLight::sample in the reference's operation order (lighting.cpp:93-104, 50-59)
+        float v2 = L.kind == IPT_LIGHT_AREA_TRIANGLE ? xmul(u2, xsub(1.0f, u1)) : xmul(u2, 1.0f);
+        f3 q = xadd3(xadd3(xscale3(mk3(L.xax, L.xay, L.xaz), u1), xscale3(mk3(L.yax, L.yay, L.yaz), v2)), mk3(L.px, L.py, L.pz));
+        f3 dir = xnormalize3(xsub3(q, pos));
+        float cosinus = xdot3(mk3(L.nx, L.ny, L.nz), neg3(dir));
+        if (cosinus < 1e-5f) return mk3(0, 0, 0);
+        return dir;
+    }
     if (AREA || L.kind <= IPT_LIGHT_AREA_TRIANGLE) {
         float v2 = L.kind == IPT_LIGHT_AREA_TRIANGLE ? pmul(u2, __fsub_rn(1.0f, u1)) : u2;
         p = mk3(__fadd_rn(pfma(L.yax, v2, pmul(L.xax, u1)), L.px), __fadd_rn(pfma(L.yay, v2, pmul(L.xay, u1)), L.py),
@@ -240,7 +298,7 @@ __device__ __forceinline__ float mix_value(const DevScene& S, const Sdf& sdf, f3
 // component whose running sum exceeds it is sampled. r >= total (float rounding; uninitialised result in the
 // reference) is a failed sample. Both candidate directions are formed by every lane (no light-vs-sdf divergence).
 // INLINE_LIGHTS: 1 = the caller knows the lights are the inline ones (compile-time), 0 = ask the scene; AREA: ... and area lights
-template <int INLINE_LIGHTS = 0, bool AREA = false, bool LAMBERT = false>
+template <int INLINE_LIGHTS = 0, bool AREA = false, bool LAMBERT = false, bool EXACT = false>
 __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, const Basis& bn, const Basis& bl, f3 pos, float us, float u1, float u2, float ul) {
     f3 wl = mk3(0, 0, 0);
     float acc = 0.0f;
@@ -250,7 +308,7 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
         for (int i = 0; i < IPT_INLINE_LIGHTS; ++i)
             if (i < (int)S.n_lights) {
                 acc = S.lights[i].cdf;
-                if (!from_light && us < acc) { from_light = true; wl = light_sample_dir<AREA>(S.lights[i], pos, u1, u2); }
+                if (!from_light && us < acc) { from_light = true; wl = light_sample_dir<AREA, EXACT>(S.lights[i], pos, u1, u2); }
             }
     } else if (!INLINE_LIGHTS && S.n_lights) {
         // first i with us < cdf[i]; cdf is non-decreasing, so a binary search finds what the linear scan finds
@@ -259,10 +317,10 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
             uint32_t mid = (lo + hi) >> 1;
             if (us < __ldg(&S.light_cdf[mid])) hi = mid; else lo = mid + 1;
         }
-        if (lo < S.n_lights) { from_light = true; wl = light_sample_dir(S.lights_g[lo], pos, u1, u2); }
+        if (lo < S.n_lights) { from_light = true; wl = light_sample_dir<false, EXACT>(S.lights_g[lo], pos, u1, u2); }
         acc = __ldg(&S.light_cdf[S.n_lights - 1]);
     }
-    f3 ws = sdf_sample<LAMBERT>(sdf, bn, bl, u1, u2, ul);
+    f3 ws = sdf_sample<LAMBERT, EXACT>(sdf, bn, bl, u1, u2, ul);
     if (from_light) return wl;
     acc += S.sdf_weight;
     if (us < acc) return ws;

@@ -50,16 +50,7 @@ int main(int argc, char** argv) {
         glm::vec3 smp = si ? si->sdf->sample() : glm::vec3();
         auto lddf = scene.lighting->distributionInPoint(glm::vec3(0.2f, -0.8f, -1.0f));
         float lval = lddf->value(glm::vec3(0, 0, 1));
-        // Gui's output stage (gui.cpp:186-194) and camera keys (gui.cpp:105-134) through the host classes
-        std::vector<float> shown = dplane.display(0.2f);
-        float shown_max = 0;
-        for (float v : shown) shown_max = v > shown_max ? v : shown_max;
-        if (argc > 3) dplane.save(argv[3]);
-        auto* cam = dynamic_cast<ipt_b200::DeviceCamera*>(const_cast<Camera*>(scene.camera.get()));
-        glm::vec3 before = cam->position;
-        cam->orbit(IPT_KEY_LEFT);
-        cam->orbit(IPT_KEY_RIGHT);
-        float orbit_err = std::fabs(cam->position.x - before.x) + std::fabs(cam->position.y - before.y) + std::fabs(cam->position.z - before.z);
+        // (rendered before the camera keys below move the camera: an orbit round trip is exact only to rounding)
         // the multi-GPU entry: the same passes split over two device slots (two GPUs when the box has them), merged on the
         // device by ipt_plane_merge, must reproduce the single-device plane
         ipt_b200::DevicePlane mplane(96, 96);
@@ -80,6 +71,16 @@ int main(int argc, char** argv) {
         }
         printf("{\"multi_devices\": [%d, %d], \"multi_paths\": %llu, \"multi_rays\": %llu, \"multi_counters_equal\": %zu, \"multi_max_rel\": %.3g}\n", slots[0],
                slots[1], (unsigned long long)mst.paths, (unsigned long long)mst.rays, multi_counters_equal, multi_max_rel);
+        // Gui's output stage (gui.cpp:186-194) and camera keys (gui.cpp:105-134) through the host classes
+        std::vector<float> shown = dplane.display(0.2f);
+        float shown_max = 0;
+        for (float v : shown) shown_max = v > shown_max ? v : shown_max;
+        if (argc > 3) dplane.save(argv[3]);
+        auto* cam = dynamic_cast<ipt_b200::DeviceCamera*>(const_cast<Camera*>(scene.camera.get()));
+        glm::vec3 before = cam->position;
+        cam->orbit(IPT_KEY_LEFT);
+        cam->orbit(IPT_KEY_RIGHT);
+        float orbit_err = std::fabs(cam->position.x - before.x) + std::fabs(cam->position.y - before.y) + std::fabs(cam->position.z - before.z);
         dplane.addRay(0.5f, 0.5f, 1.0f);
         printf("{\"display_max\": %.9g, \"orbit_round_trip_error\": %.9g}\n", shown_max, orbit_err);
         printf("{\"scene\": \"%s\", \"paths\": %llu, \"rays\": %llu, \"mean_device_plane\": %.9g, \"count_device_plane\": %zu, "

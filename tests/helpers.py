@@ -46,34 +46,41 @@ def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def _oracle_render_worker(args):
-    scene, kw, seed, pass_begin, pass_count, use_bvh = args
-    import oracle_lib
-    from ipt_b200 import capi
-
-    sd = capi.SceneDescription(scene)
-    p = capi.default_params(pass_begin=pass_begin, pass_count=pass_count, seed=seed, **kw)
-    o = oracle_lib.load_oracle().render(sd.ptr, p, oracle_lib.RNG_PHILOX, use_bvh)
-    return o["sum"], o["sumsq"], o["counters"], o["rays"]
-
-
-def oracle_render_parallel(scene, passes, seed, use_bvh=0, workers=None, **kw):
+def oracle_render_parallel(scene, passes, seed, use_bvh=0, workers=None, timeout=900, **kw):
     """The oracle's Philox-mode render (test infrastructure: the CPU checker) of `passes` passes, split into contiguous pass
-    ranges over forked single-threaded processes (Philox counters are keyed by (pixel, pass, node), so the ranges are
-    disjoint streams and the merged accumulators equal a single render). Returns dict(sum, sumsq, count, rays)."""
-    import multiprocessing as mp
+    ranges over single-threaded worker PROCESSES started from scratch (tests/oracle_worker.py; a fork of a process that has
+    initialised CUDA is not safe). Philox counters are keyed by (pixel, pass, node), so the ranges are disjoint streams and
+    the merged accumulators equal a single render. Returns dict(sum, sumsq, count, rays)."""
+    import json
     import os
+    import subprocess
+    import sys
+    import tempfile
+    from pathlib import Path
 
     workers = max(1, min(workers or (os.cpu_count() or 1), passes))
     base, extra = divmod(passes, workers)
-    jobs, begin = [], 0
-    for r in range(workers):
-        n = base + (1 if r < extra else 0)
-        jobs.append((scene, kw, seed, begin, n, use_bvh))
-        begin += n
-    with mp.get_context("fork").Pool(workers) as pool:
-        res = pool.map(_oracle_render_worker, jobs)
-    return dict(sum=sum(r[0] for r in res), sumsq=sum(r[1] for r in res), count=sum(r[2] for r in res), rays=sum(r[3] for r in res))
+    worker = str(Path(__file__).resolve().parent / "oracle_worker.py")
+    with tempfile.TemporaryDirectory() as tmp:
+        procs, begin = [], 0
+        for r in range(workers):
+            n = base + (1 if r < extra else 0)
+            out = os.path.join(tmp, f"part{r}.npz")
+            procs.append((subprocess.Popen([sys.executable, worker, scene, json.dumps(kw), str(seed), str(begin), str(n), str(use_bvh), out],
+                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), out))
+            begin += n
+        parts = []
+        try:
+            for pr, out in procs:
+                log, _ = pr.communicate(timeout=timeout)
+                assert pr.returncode == 0, log[-2000:]
+                parts.append(dict(np.load(out)))
+        finally:
+            for pr, _ in procs:
+                if pr.poll() is None:
+                    pr.kill()
+    return dict(sum=sum(p["sum"] for p in parts), sumsq=sum(p["sumsq"] for p in parts), count=sum(p["count"] for p in parts),
+                rays=int(sum(int(p["rays"]) for p in parts)))
 
 
 def block_sums(a, block):

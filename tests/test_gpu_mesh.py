@@ -129,7 +129,7 @@ def test_mesh_image_z_test_against_oracle(scene, size, depth, schedule, cpu_pass
     sc = capi.Scene(sd)
     kw = dict(width=size, height=size, depth_max=depth, schedule=schedule)
     o = oracle_render_parallel(scene, cpu_passes, seed=1234, use_bvh=1, **kw)
-    s, q, cnt, st = sc.render_host(capi.default_params(pass_count=gpu_passes, seed=98765, **kw))
+    s, q, cnt, st = sc.render_host(capi.default_params(pass_count=gpu_passes, seed=98765, flags=capi.FLAG_KEEP_ZERO_WEIGHT, **kw))  # count rays like the oracle
     assert same_coverage(cnt, gpu_passes, o["count"], cpu_passes)
     g = dict(sum=block_sums(o["sum"], block), sumsq=block_sums(o["sumsq"], block), count=block_sums(o["count"], block))
     r = image_stats(block_sums(s.astype(np.float64), block), block_sums(q.astype(np.float64), block), block_sums(cnt.astype(np.uint64), block), g,

@@ -55,6 +55,37 @@ def test_trace_batch_bit_exact(name, scenes, oracle):
     assert np.array_equal(g["outcome"], c["outcome"])
 
 
+@pytest.mark.parametrize("name", ["smallpt", "box", "cornell", "fractal", "openspheres"])
+def test_rays_starting_on_surfaces_bit_exact(name, scenes, oracle):
+    """Three generations of rays that START on a surface (the hit point of the previous generation, random directions in
+    the hemisphere of its normal): the regime every secondary ray of a render lives in. GeometrySmallPt's radius-1000
+    spheres with eps = 1e-4 (GeometrySmallPt.cpp:17-22) make 11 % of such rays hit the very wall they start on, decided by
+    the float rounding of the start point; the device agrees with the oracle bit for bit there too."""
+    sd, sc = scenes(name)
+    rng = np.random.default_rng(3)
+    o, d = oracle.camera_rays(sd.ptr, rng.random((20000, 2)).astype(np.float32))
+    first = oracle.trace_batch(sd.ptr, o, d)
+    hit = first["outcome"] == 1
+    pos, nrm = first["pos"][hit], first["normal"][hit]
+    assert len(pos) > 2000
+    self_hits = 0
+    for generation in range(3):
+        v = rng.normal(size=pos.shape).astype(np.float32)
+        v /= np.linalg.norm(v, axis=1, keepdims=True).astype(np.float32)
+        flip = (v * nrm).sum(1) < 0
+        v[flip] = -v[flip]
+        v = np.ascontiguousarray(v, np.float32)
+        g = sc.trace_batch(pos, v)
+        c = oracle.trace_batch(sd.ptr, pos, v)
+        assert np.array_equal(g["prim"], c["prim"]) and np.array_equal(bits(g["t"]), bits(c["t"]))
+        assert np.array_equal(g["outcome"], c["outcome"]) and np.array_equal(g["light"], c["light"])
+        self_hits += int(((c["t"] < 1e-2) & (c["outcome"] == 1)).sum())
+        ok = c["outcome"] == 1
+        pos, nrm = c["pos"][ok], c["normal"][ok]
+    if name == "smallpt":
+        assert self_hits > 1000  # the self-intersection regime is really exercised
+
+
 def _render_pair(sd, sc, oracle, **kw):
     p = capi.default_params(**kw)
     s, q, cnt, st = sc.render_host(p)
@@ -94,7 +125,7 @@ def test_full_tree_render_matches_oracle_with_common_random_numbers(name, res, s
     scale = max(ref.max(), 1e-12)
     diff = s - ref
     same = np.abs(diff) / scale <= 1e-5
-    assert same.mean() > 0.5
+    assert same.mean() > 0.85
     # flips are rare events on both sides with the same distribution: the mean difference is noise around 0
     d = diff[~same]
     if d.size > 20:
