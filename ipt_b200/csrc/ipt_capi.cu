@@ -100,6 +100,7 @@ struct ipt_scene {
     DevPrim* d_prims = nullptr;
     DevLight* d_lights = nullptr;
     float* d_light_cdf = nullptr;
+    uint32_t* d_light_guide = nullptr;
     DevMaterial* d_mats = nullptr;
     LbvhDevice bvh{};
     LbvhDevice light_bvh{};
@@ -406,6 +407,7 @@ static int occupancy_grid(K kernel, int sm_count, size_t smem) {
     } while (0)
 
 static size_t stack_smem(const ipt_scene* s) { return s->mesh ? (size_t)IPT_STACK_SHORT * IPT_BLOCK * sizeof(uint32_t) : 0; }
+static size_t mesh_smem(const ipt_scene* s) { return s->mesh ? (size_t)IPT_MESH_SMEM_BYTES : 0; } // k_extend_mesh: stacks + the per-warp ray pools
 
 template <class T>
 struct DevBuf {
@@ -519,6 +521,16 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
         for (size_t i = 0; i < lights.size(); ++i) cdf[i] = lights[i].cdf;
         CUDA_TRY(upload(s->d_light_cdf, cdf));
         dv.light_cdf = s->d_light_cdf;
+        // guide[b] = first i with b / M < cdf[i] (DevScene::light_guide); b / M is exact in float
+        std::vector<uint32_t> guide(IPT_LIGHT_GUIDE + 2);
+        size_t i = 0;
+        for (uint32_t b = 0; b <= IPT_LIGHT_GUIDE + 1; ++b) {
+            const float edge = (float)b / (float)IPT_LIGHT_GUIDE;
+            while (i < cdf.size() && !(edge < cdf[i])) ++i;
+            guide[b] = (uint32_t)i;
+        }
+        CUDA_TRY(upload(s->d_light_guide, guide));
+        dv.light_guide = s->d_light_guide;
     }
     dv.mats_g = s->d_mats;
     for (uint32_t i = 0; i < desc->n_prims && i < IPT_INLINE_PRIMS; ++i) dv.prims[i] = prims[i];
@@ -580,6 +592,8 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
             if (lbvh_build(ltris.data(), desc->n_lights, s->stream, s->light_bvh, err, extra.data()) != 0)
                 return fail(IPT_ERR_CUDA, "light LBVH build failed: " + err);
             dv.light_nodes = s->light_bvh.nodes;
+            dv.light_qnodes = s->light_bvh.qnodes;
+            dv.light_grid = s->light_bvh.grid;
             dv.light_recs = s->light_bvh.tri_records;
             dv.n_light_bvh = desc->n_lights;
         }
@@ -608,8 +622,9 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     s->grid_accumulate = occupancy_grid(k_accumulate, s->sm_count, 0);
     if (s->mesh && !s->smallpt) {
         s->mesh_box_scene = s->inline_area_light && dv.planes_grouped && dv.others_inline;
-        s->grid_mesh = s->mesh_box_scene ? occupancy_grid(k_extend_mesh<false, SPEC_BOX_SCENE>, s->sm_count, sm) : occupancy_grid(k_extend_mesh<false>, s->sm_count, sm);
-        s->grid_mesh_last = s->mesh_box_scene ? occupancy_grid(k_extend_mesh<true, SPEC_BOX_SCENE>, s->sm_count, sm) : occupancy_grid(k_extend_mesh<true>, s->sm_count, sm);
+        const size_t msm = mesh_smem(s);
+        s->grid_mesh = s->mesh_box_scene ? occupancy_grid(k_extend_mesh<false, SPEC_BOX_SCENE>, s->sm_count, msm) : occupancy_grid(k_extend_mesh<false>, s->sm_count, msm);
+        s->grid_mesh_last = s->mesh_box_scene ? occupancy_grid(k_extend_mesh<true, SPEC_BOX_SCENE>, s->sm_count, msm) : occupancy_grid(k_extend_mesh<true>, s->sm_count, msm);
     }
 #define OCC(SP, MS)                                                                          \
     s->grid_extend = occupancy_grid(k_extend<SP, MS, false>, s->sm_count, sm);               \
@@ -635,7 +650,7 @@ int ipt_scene_destroy(ipt_scene* s) {
     free_workspace(s->ws);
     lbvh_free(s->bvh);
     lbvh_free(s->light_bvh);
-    cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_light_cdf); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
+    cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_light_cdf); cudaFree(s->d_light_guide); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
     if (s->pinned) cudaFreeHost(s->pinned);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -1201,6 +1216,7 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, sizeof(unsigned long long) * ST_COUNT, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev_begin, s->stream));
     size_t sm = stack_smem(s);
+    const size_t msm = mesh_smem(s);
     uint32_t batches = 0;
     for (uint64_t g0 = 0; g0 < total_paths; g0 += batch, ++batches) {
         C.g0 = g0;
@@ -1228,12 +1244,12 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
             if (persistent_mesh) {
                 // mesh scenes: persistent warps that refill idle lanes from the ray queue (ipt_trace.cuh)
                 if (last) {
-                    if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<true, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
-                    else TIMED(1, (k_extend_mesh<true><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                    if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<true, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
+                    else TIMED(1, (k_extend_mesh<true><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
                     break;
                 }
-                if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<false, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
-                else TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)));
+                if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<false, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
+                else TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
                 int gs2 = std::max(1, std::min(s->grid_shade, cap_blocks));
                 TIMED(2, (k_shade<FUSE_NONE, false><<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
                 continue;

@@ -193,6 +193,47 @@ __device__ __forceinline__ bool light_box(const f8& a, int base, f3 o, f3 inv, f
     return tn <= tf * 1.0000003f && tn <= limit;
 }
 
+// ---- the light LBVH through its 32-byte quantised nodes (BvhNodeQ, see ipt_device.cuh) -----------------------------------------
+// Same node format and grid space as the mesh traversal (ipt_trace.cuh), but a ray towards the lights starts anywhere in the
+// scene, possibly many box extents away from the (often flat) root box of the lights, where the float error of the mapped
+// origin o' is no longer small against a grid cell. The test therefore carries a per-axis slack s = |o'| |1/d'| 2^-20 — twice
+// the bound on the accumulated rounding error of t = g / d' - o' / d' that grows with |o'|; the part that does not is covered
+// by the full cell every quantised box is padded with — folded into the two constants of the fused multiply-adds: the
+// entry distance of an axis is g_near / d' + (c - s), the exit distance g_far / d' + (c + s), with the near / far plane
+// chosen by the sign of the direction (a select instead of the min / max of the symmetric form). Conservative for any
+// origin; a direction component of 0 gets 1/d' = +-1e37 as in grid_ray.
+#ifndef IPT_LIGHT_QNODES
+#define IPT_LIGHT_QNODES 0 // 1: traverse the light LBVH through its 32-byte nodes. Measured (profiles/tuning_r02.md): same node visits, C5 unchanged, 100 emitters -12 % (the walk waits on dependent loads, not on L1 sectors, and the decode costs issue slots): off
+#endif
+struct LightGridRay {
+    f3 inv, cn, cf;
+    bool nx, ny, nz; // direction component negative: the box's upper plane is the near one
+};
+__device__ __forceinline__ LightGridRay light_grid_ray(const GridMap& G, f3 o, f3 d) {
+    LightGridRay r;
+    float ox = __fmaf_rn(__fsub_rn(o.x, G.lo[0]), G.scale[0], IPT_GRID_BASE), oy = __fmaf_rn(__fsub_rn(o.y, G.lo[1]), G.scale[1], IPT_GRID_BASE),
+          oz = __fmaf_rn(__fsub_rn(o.z, G.lo[2]), G.scale[2], IPT_GRID_BASE);
+    float dx = d.x * G.scale[0], dy = d.y * G.scale[1], dz = d.z * G.scale[2];
+    r.inv = mk3(copysignf(fminf(fabsf(1.0f / dx), 1e37f), dx), copysignf(fminf(fabsf(1.0f / dy), 1e37f), dy), copysignf(fminf(fabsf(1.0f / dz), 1e37f), dz));
+    float cx = -ox * r.inv.x, cy = -oy * r.inv.y, cz = -oz * r.inv.z;
+    const float k = 9.5367431640625e-07f; // 2^-20
+    float sx = fabsf(cx) * k, sy = fabsf(cy) * k, sz = fabsf(cz) * k; // |c| = |o'| |1/d'|
+    r.cn = mk3(cx - sx, cy - sy, cz - sz);
+    r.cf = mk3(cx + sx, cy + sy, cz + sz);
+    r.nx = r.inv.x < 0.0f; r.ny = r.inv.y < 0.0f; r.nz = r.inv.z < 0.0f;
+    return r;
+}
+// one child box of a BvhNodeQ: wa = lo.x | lo.y, wb = lo.z | hi.x, wc = hi.y | hi.z; true = the ray may hit it before `limit`
+__device__ __forceinline__ bool light_box_q(uint32_t wa, uint32_t wb, uint32_t wc, const LightGridRay& R, float limit) {
+    float lox = grid_lo16(wa), loy = grid_hi16(wa), loz = grid_lo16(wb), hix = grid_hi16(wb), hiy = grid_lo16(wc), hiz = grid_hi16(wc);
+    float tnx = __fmaf_rn(R.nx ? hix : lox, R.inv.x, R.cn.x), tfx = __fmaf_rn(R.nx ? lox : hix, R.inv.x, R.cf.x);
+    float tny = __fmaf_rn(R.ny ? hiy : loy, R.inv.y, R.cn.y), tfy = __fmaf_rn(R.ny ? loy : hiy, R.inv.y, R.cf.y);
+    float tnz = __fmaf_rn(R.nz ? hiz : loz, R.inv.z, R.cn.z), tfz = __fmaf_rn(R.nz ? loz : hiz, R.inv.z, R.cf.z);
+    float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    float tf = fminf(fminf(tfx, tfy), tfz);
+    return tn <= tf * 1.0000003f && tn <= limit;
+}
+
 // One stack traversal of the light LBVH serving both queries of CollectionLighting:
 //   LQ_NEAREST: traceRayToLight (CollectionLighting.cpp:23-34): nearest hit by length(pos - origin), earliest index on ties
 //   LQ_PDF:     the mixture density sum_i w_i * DdfFromLight_i::value(d) over ALL lights the ray hits (ddf.cpp:156-162)
@@ -206,7 +247,11 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
     float pdf_sum = 0.0f;
     best_len = IPT_INF;
     which = IPT_NO_HIT;
+#if IPT_LIGHT_QNODES
+    const LightGridRay R = light_grid_ray(S.light_grid, o, d);
+#else
     f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+#endif
     float dlen = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
     uint32_t stack[IPT_LBVH_MAX_HEIGHT];
     int sp = 0;
@@ -235,13 +280,19 @@ __device__ __forceinline__ float light_bvh_query(const DevScene& S, f3 o, f3 d, 
             }
             node = IPT_NO_HIT;
         } else {
-            f8 n0 = ldg256(&S.light_nodes[node]);
-            f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[node]) + 32);
             ++tc.light_nodes;
             // entry distances are in units of t; a hit at length L has t = L / |d|
             float limit = MODE == LQ_NEAREST ? (best_len / dlen) * 1.0001f + 1e-6f : IPT_INF;
+#if IPT_LIGHT_QNODES
+            u8x32 q = ldg256u(&S.light_qnodes[node]);
+            bool h0 = light_box_q(q.v[0], q.v[1], q.v[2], R, limit), h1 = light_box_q(q.v[3], q.v[4], q.v[5], R, limit);
+            uint32_t left = q.v[6], right = q.v[7];
+#else
+            f8 n0 = ldg256(&S.light_nodes[node]);
+            f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[node]) + 32);
             bool h0 = light_box(n0, 0, o, inv, limit), h1 = light_box(n1, 0, o, inv, limit);
             uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
+#endif
             node = IPT_NO_HIT;
             if (h0 && h1) { node = left; stack[sp++] = right; }
             else if (h0) node = left;
@@ -490,10 +541,16 @@ __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCt
 // First node visit of the light LBVH: false = the ray misses both root boxes, i.e. there is no light along it.
 __device__ __forceinline__ bool light_root_hit(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
     ++tc.light_nodes;
+#if IPT_LIGHT_QNODES
+    const LightGridRay R = light_grid_ray(S.light_grid, o, d);
+    u8x32 q = ldg256u(&S.light_qnodes[0]);
+    return light_box_q(q.v[0], q.v[1], q.v[2], R, IPT_INF) || light_box_q(q.v[3], q.v[4], q.v[5], R, IPT_INF);
+#else
     f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     f8 n0 = ldg256(&S.light_nodes[0]);
     f8 n1 = ldg256(reinterpret_cast<const char*>(&S.light_nodes[0]) + 32);
     return light_box(n0, 0, o, inv, IPT_INF) || light_box(n1, 0, o, inv, IPT_INF);
+#endif
 }
 // Many-light scenes, last traced depth: the whole of trace_scene_last for a parked ray (light LBVH walk, weight, and the
 // occlusion test if a light was reached). Parked are only rays that passed light_root_hit, so the lanes of a pop walk

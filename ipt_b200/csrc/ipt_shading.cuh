@@ -312,7 +312,9 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
             }
     } else if (!INLINE_LIGHTS && S.n_lights) {
         // first i with us < cdf[i]; cdf is non-decreasing, so a binary search finds what the linear scan finds
-        uint32_t lo = 0, hi = S.n_lights;
+        // (the guide table narrows the range to the bucket of us first, see DevScene::light_guide)
+        const uint32_t bucket = (uint32_t)(us * (float)IPT_LIGHT_GUIDE);
+        uint32_t lo = __ldg(&S.light_guide[bucket]), hi = min(__ldg(&S.light_guide[bucket + 1]) + 1u, S.n_lights);
         while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
             if (us < __ldg(&S.light_cdf[mid])) hi = mid; else lo = mid + 1;

@@ -14,6 +14,8 @@ VARIANTS = {
     "nearr1": ["IPT_FAST_SECONDARY=0", "IPT_U01_BITS=24", "IPT_PHILOX_ROUNDS=10", "IPT_BVH_WIDE_NODES=1", "IPT_LIGHT_TWO_QUEUES=0"],
     "wide": ["IPT_BVH_WIDE_NODES=1"],      # mesh traversal over the 64-byte float nodes
     "oneq": ["IPT_LIGHT_TWO_QUEUES=0"],    # many-light scenes: a single park queue at the non-last depths
+    "lightq": ["IPT_LIGHT_QNODES=1"],      # light LBVH through its 32-byte quantised nodes (measured: no gain)
+    "meshv1": ["IPT_MESH_POOLS=0"],        # the round-1 mesh traversal kernel (no ready / done pools)
     "bounds": ["IPT_DEBUG_BOUNDS"],        # every queue append checked against its capacity (compute-sanitizer is closed on this pool)
 }
 if __name__ == "__main__":
