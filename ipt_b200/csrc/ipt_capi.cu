@@ -101,6 +101,7 @@ struct ipt_scene {
     DevLight* d_lights = nullptr;
     float* d_light_cdf = nullptr;
     uint32_t* d_light_guide = nullptr;
+    float* d_light_samp = nullptr;
     DevMaterial* d_mats = nullptr;
     LbvhDevice bvh{};
     LbvhDevice light_bvh{};
@@ -531,6 +532,16 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
         }
         CUDA_TRY(upload(s->d_light_guide, guide));
         dv.light_guide = s->d_light_guide;
+        std::vector<float> samp(16 * lights.size());
+        for (size_t k = 0; k < lights.size(); ++k) {
+            const DevLight& L = lights[k];
+            float kind_bits;
+            std::memcpy(&kind_bits, &L.kind, 4);
+            const float rec[16] = {L.px, L.py, L.pz, kind_bits, L.xax, L.xay, L.xaz, L.radius, L.yax, L.yay, L.yaz, 0.0f, L.nx, L.ny, L.nz, 0.0f};
+            std::memcpy(&samp[16 * k], rec, sizeof rec);
+        }
+        CUDA_TRY(upload(s->d_light_samp, samp));
+        dv.light_samp = reinterpret_cast<const float4*>(s->d_light_samp);
     }
     dv.mats_g = s->d_mats;
     for (uint32_t i = 0; i < desc->n_prims && i < IPT_INLINE_PRIMS; ++i) dv.prims[i] = prims[i];
@@ -559,6 +570,27 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
     s->smallpt = smallpt;
     s->mesh = desc->n_triangles > 0;
     s->geom_fast = !smallpt && !s->mesh && dv.planes_grouped && dv.others_inline;
+    // Shadow rays of box scenes skip the wall planes (DevScene::lights_inside_box): every non-plane primitive is a sphere
+    // inside the closed box [-1,1]^3 and every light is an area light whose corners keep a margin of 1e-3 to every wall, so
+    // origin (a point of a wall or of a sphere) and target lie in the convex box and no wall can come between them.
+    dv.lights_inside_box = 0;
+    if (s->geom_fast && s->inline_area_light && dv.n_planes > 0) {
+        bool inside = true;
+        for (uint32_t k = 0; k < dv.n_others; ++k) {
+            const DevSphere& sp = dv.others[k];
+            const float r = std::sqrt(sp.r2);
+            for (float c : {sp.cx, sp.cy, sp.cz}) inside = inside && std::fabs(c) + r <= 1.0f;
+        }
+        for (uint32_t i = 0; i < desc->n_lights; ++i) {
+            const ipt_light& l = desc->lights[i];
+            for (int corner = 0; corner < 4; ++corner)
+                for (int a = 0; a < 3; ++a) {
+                    const float q = l.position[a] + ((corner & 1) ? l.x_axis[a] : 0.0f) + ((corner & 2) ? l.y_axis[a] : 0.0f);
+                    inside = inside && std::fabs(q) <= 1.0f - 1e-3f;
+                }
+        }
+        dv.lights_inside_box = inside ? 1u : 0u;
+    }
     s->all_lambert = true;
     for (const DevMaterial& m : mats) if (m.ddf != IPT_DDF_COSINE) s->all_lambert = false;
     if (s->mesh) {
@@ -650,7 +682,7 @@ int ipt_scene_destroy(ipt_scene* s) {
     free_workspace(s->ws);
     lbvh_free(s->bvh);
     lbvh_free(s->light_bvh);
-    cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_light_cdf); cudaFree(s->d_light_guide); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
+    cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_light_cdf); cudaFree(s->d_light_guide); cudaFree(s->d_light_samp); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
     if (s->pinned) cudaFreeHost(s->pinned);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);

@@ -40,6 +40,9 @@
 #else
 #define IPT_BOUNDS_OK(index, capacity, stats) true
 #endif
+#ifndef IPT_SHADOW_SKIP_WALLS
+#define IPT_SHADOW_SKIP_WALLS 1 // 0: shadow rays of box scenes intersect the wall planes too (tuning A/B only)
+#endif
 #ifndef IPT_LIGHT_TWO_QUEUES
 #define IPT_LIGHT_TWO_QUEUES 1 // 0: one park queue for every child of a many-light scene (tuning A/B only)
 #endif
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DevSce
 // ---- closest hit over the whole scene (Geometry::traceRay) ------------------------------------------
 
 template <bool SMALLPT, bool MESH, bool GFAST = false, bool X = true>
-__device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc);
+__device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc, bool skip_planes = false);
 
 // ---- nearest light (CollectionLighting::traceRayToLight, src/CollectionLighting.cpp:23-34) -----------
 template <bool PDF, bool AREA = false, bool X = true, class LightRef>
@@ -531,7 +534,8 @@ __device__ __forceinline__ void resolve_parked(const DevScene& S, const RenderCt
     f3 o = mk3(dq[0 * IPT_PARK + k], dq[1 * IPT_PARK + k], dq[2 * IPT_PARK + k]);
     f3 d = mk3(dq[3 * IPT_PARK + k], dq[4 * IPT_PARK + k], dq[5 * IPT_PARK + k]);
     float ldist = dq[6 * IPT_PARK + k];
-    SurfHit sh = trace_geometry<SMALLPT, false, IPT_SPEC_FAST_GEOMETRY(SPEC), X>(S, o, d, tc);
+    // the ray reached a light: only what can lie between the origin and that light has to be intersected
+    SurfHit sh = trace_geometry<SMALLPT, false, IPT_SPEC_FAST_GEOMETRY(SPEC), X>(S, o, d, tc, IPT_SHADOW_SKIP_WALLS && IPT_SPEC_FAST_GEOMETRY(SPEC) && S.lights_inside_box != 0);
     if (light_nearer<X>(sh, o, d, ldist)) {
         ++n_light;
         atomicAdd(&C.pathval[__float_as_uint(dq[8 * IPT_PARK + k])], dq[7 * IPT_PARK + k]);

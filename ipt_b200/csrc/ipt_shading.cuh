@@ -319,7 +319,20 @@ __device__ __forceinline__ f3 mix_sample(const DevScene& S, const Sdf& sdf, cons
             uint32_t mid = (lo + hi) >> 1;
             if (us < __ldg(&S.light_cdf[mid])) hi = mid; else lo = mid + 1;
         }
-        if (lo < S.n_lights) { from_light = true; wl = light_sample_dir<false, EXACT>(S.lights_g[lo], pos, u1, u2); }
+#ifndef IPT_LIGHT_SAMP_RECORDS
+#define IPT_LIGHT_SAMP_RECORDS 1 // 0: sample from the 112-byte DevLight record (tuning A/B only)
+#endif
+        if (!IPT_LIGHT_SAMP_RECORDS && lo < S.n_lights) { from_light = true; wl = light_sample_dir<false, EXACT>(S.lights_g[lo], pos, u1, u2); }
+        else if (lo < S.n_lights) {
+            from_light = true;
+            f8 r0 = ldg256(&S.light_samp[4 * (size_t)lo]), r1 = ldg256(&S.light_samp[4 * (size_t)lo + 2]);
+            DevLight L; // only the fields Light::sample reads
+            L.px = r0.v[0]; L.py = r0.v[1]; L.pz = r0.v[2]; L.kind = __float_as_uint(r0.v[3]);
+            L.xax = r0.v[4]; L.xay = r0.v[5]; L.xaz = r0.v[6]; L.radius = r0.v[7];
+            L.yax = r1.v[0]; L.yay = r1.v[1]; L.yaz = r1.v[2];
+            L.nx = r1.v[4]; L.ny = r1.v[5]; L.nz = r1.v[6];
+            wl = light_sample_dir<false, EXACT>(L, pos, u1, u2);
+        }
         acc = __ldg(&S.light_cdf[S.n_lights - 1]);
     }
     f3 ws = sdf_sample<LAMBERT, EXACT>(sdf, bn, bl, u1, u2, ul);

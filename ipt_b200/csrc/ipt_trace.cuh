@@ -168,9 +168,11 @@ extern __shared__ uint32_t ipt_dyn_smem[];
 // X = false: contracted arithmetic in the grouped-plane / inline-sphere branch (secondary rays, see ipt_device.cuh); the
 // generic ordered scans keep the exact routines
 template <bool SMALLPT, bool GFAST = false, bool X = true>
-__device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, double& dist_d, float& dist_f, uint32_t& best) {
+__device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, double& dist_d, float& dist_f, uint32_t& best, bool skip_planes = false) {
     if (GFAST || (!SMALLPT && S.planes_grouped)) {
-        if (S.n_planes) {
+        // skip_planes (warp-uniform): an occlusion test towards a light that lies strictly inside the convex box the planes
+        // bound (DevScene::lights_inside_box): the segment to the light cannot cross a wall, only the other primitives matter
+        if (S.n_planes && !skip_planes) {
             isect_axis_planes<X, 0>(S.plane_of[0], S.plane_of[1], o.x, d.x, o, d, dist_f, best);
             isect_axis_planes<X, 1>(S.plane_of[2], S.plane_of[3], o.y, d.y, o, d, dist_f, best);
             isect_axis_planes<X, 2>(S.plane_of[4], S.plane_of[5], o.z, d.z, o, d, dist_f, best);
@@ -196,11 +198,11 @@ __device__ __forceinline__ void analytic_closest(const DevScene& S, f3 o, f3 d, 
 }
 
 template <bool SMALLPT, bool MESH, bool GFAST, bool X>
-__device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc) {
+__device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d, TraceCounters& tc, bool skip_planes) {
     double dist_d = (double)IPT_INF;
     float dist_f = IPT_INF;
     uint32_t best = IPT_NO_HIT;
-    analytic_closest<SMALLPT, GFAST, X>(S, o, d, dist_d, dist_f, best);
+    analytic_closest<SMALLPT, GFAST, X>(S, o, d, dist_d, dist_f, best, skip_planes);
     SurfHit r;
     r.prim = best;
     r.tri_pos = IPT_NO_HIT;

@@ -15,6 +15,8 @@ VARIANTS = {
     "wide": ["IPT_BVH_WIDE_NODES=1"],      # mesh traversal over the 64-byte float nodes
     "oneq": ["IPT_LIGHT_TWO_QUEUES=0"],    # many-light scenes: a single park queue at the non-last depths
     "lightq": ["IPT_LIGHT_QNODES=1"],      # light LBVH through its 32-byte quantised nodes (measured: no gain)
+    "nosamp": ["IPT_LIGHT_SAMP_RECORDS=0"], # light sampling from the 112-byte records
+    "walls": ["IPT_SHADOW_SKIP_WALLS=0"],  # shadow rays of box scenes test the wall planes too
     "meshv1": ["IPT_MESH_POOLS=0"],        # the round-1 mesh traversal kernel (no ready / done pools)
     "bounds": ["IPT_DEBUG_BOUNDS"],        # every queue append checked against its capacity (compute-sanitizer is closed on this pool)
 }
