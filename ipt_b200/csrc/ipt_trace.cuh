@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                 if (lights_inline<SPEC>(S)) lh = trace_lights<false, SPEC>(S, fo, fd, lwhich, lpos, lpdf, ldist, tcl);
                 else lh = trace_lights<true, SPEC>(S, fo, fd, lwhich, lpos, lpdf, ldist, tcl);
                 // single inline light: its density follows from the hit position that is kept anyway
+                static_assert(IPT_INLINE_LIGHTS == 1, "the lights[0] shortcut below assumes that 'inline lights' means exactly one light");
                 if (lights_inline<SPEC>(S) && lh && S.n_lights) lpdf = S.lights[0].weight * light_pdf_at<IPT_SPEC_AREA_LIGHTS(SPEC)>(S.lights[0], fo, lpos);
                 const bool sh = prim != IPT_NO_HIT;
 #ifdef IPT_DEBUG_PRINT
