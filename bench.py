@@ -473,8 +473,13 @@ def roofline_block(m, w, args):
         except Exception:
             pass
     traffic = block["traffic"]
-    block["binding"] = ("instruction issue (model bytes are credited, not moved: the fused kernels keep the rays on chip)"
-                        if traffic is not None and traffic < 0.5 * block["algorithmic_bytes_per_launch"] else "hbm / L2 latency")
+    if traffic is not None and traffic < 0.5 * block["algorithmic_bytes_per_launch"]:
+        # the model's bytes are credited, not moved through HBM: ncu's DRAM traffic is far below them
+        block["binding"] = ("instruction issue (the fused shade kernels trace the rays they spawn: the ray queue the model credits is never written)"
+                            if dom == "shade" and fused else
+                            "instruction issue + dependent L2 loads (the BVH / light records the model credits are L2-resident, not HBM traffic)")
+    else:
+        block["binding"] = "hbm / L2 latency (no profile-time traffic figure for this workload)" if traffic is None else "hbm / L2 latency"
     return block
 
 
