@@ -38,7 +38,7 @@ WORKLOADS = {
                text="default scene of src/sample_scenes.cpp (make_scene_box: open unit box + sphere + one square light)"),
     "c2": dict(config="configs[1]", scene="cornell", width=1024, height=1024, depth_max=4, schedule=[16, 8, 4, 2], spp_total=1024, passes_per_step=8,
                text="Cornell-box-style scene 'cornell' (5 box planes, Lambert sphere, glossy sphere, ceiling area light)"),
-    "c3": dict(config="configs[2]", scene="mesh:1000000", width=1920, height=1080, depth_max=8, schedule=[1] * 8, spp_total=256, passes_per_step=4,
+    "c3": dict(config="configs[2]", scene="mesh:1000000", width=1920, height=1080, depth_max=8, schedule=[1] * 8, spp_total=256, passes_per_step=16,
                text="procedural 1M-triangle random mesh inside the open box, max depth 8"),
     "c4": dict(config="configs[3]", scene="mesh:10000000", width=3840, height=2160, depth_max=8, schedule=[1] * 8, spp_total=4096, passes_per_step=4,
                text="10M-triangle synthetic mesh, sample-sharded across the GPUs"),
