@@ -23,6 +23,11 @@
 using namespace iptd;
 
 #define IPT_LIGHT_BVH_MIN 8 // light sets larger than this get an LBVH
+#ifndef IPT_RENDER_LANES
+#define IPT_RENDER_LANES 1 // 2: mesh scenes keep two batches in flight on two streams (ipt_render). Measured (profiles/tuning_r02.md):
+                           // C3 397 -> 411, C4 339 -> 347 Mpaths/s with two full 2^25-path batches, nothing when the job has to be
+                           // split in two for it, and per-kernel CUDA-event times lose their meaning under the overlap: off
+#endif
 #define IPT_CNT_WORDS (3 * IPT_MAX_DEPTH + 2) // ray counts, hit counts, persistent-kernel fetch cursors
 
 // ---------------------------------------------------------------------------------------------------
@@ -111,6 +116,9 @@ struct ipt_scene {
     bool all_lambert = false;       // every material is the cosine DDF
     bool mesh_box_scene = false;    // mesh scene whose lights / analytic primitives allow k_extend_mesh<.., SPEC_BOX_SCENE>
     Workspace ws;
+    Workspace ws2;                  // second lane of ipt_render (mesh scenes: two batches in flight, see ipt_render)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_join = nullptr;
     uint32_t* d_cnt = nullptr;
     unsigned long long* d_stats = nullptr;
     std::vector<cudaEvent_t> events;
@@ -630,7 +638,9 @@ int ipt_scene_create(const ipt_scene_desc* desc, int device, ipt_scene** out) {
             dv.n_light_bvh = desc->n_lights;
         }
     }
-    CUDA_TRY(cudaMalloc((void**)&s->d_cnt, sizeof(uint32_t) * IPT_CNT_WORDS));
+    CUDA_TRY(cudaMalloc((void**)&s->d_cnt, sizeof(uint32_t) * IPT_CNT_WORDS * 2)); // one set of queue counters per lane of ipt_render
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc((void**)&s->d_stats, sizeof(unsigned long long) * ST_COUNT));
 
     size_t sm = stack_smem(s);
@@ -679,7 +689,11 @@ int ipt_scene_destroy(ipt_scene* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->host_plane) ipt_plane_destroy(s->host_plane);
+    if (s->stream2) cudaStreamSynchronize(s->stream2);
     free_workspace(s->ws);
+    free_workspace(s->ws2);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     lbvh_free(s->bvh);
     lbvh_free(s->light_bvh);
     cudaFree(s->d_prims); cudaFree(s->d_lights); cudaFree(s->d_light_cdf); cudaFree(s->d_light_guide); cudaFree(s->d_light_samp); cudaFree(s->d_mats); cudaFree(s->d_cnt); cudaFree(s->d_stats);
@@ -1108,10 +1122,10 @@ static size_t workspace_bytes(size_t ray_cap, size_t hit_cap, size_t path_cap, b
     return 36 * ray_cap + 32 * std::max<size_t>(hit_cap, 1) * (two_hit_sets ? 2 : 1) + 4 * path_cap;
 }
 // IPT_OK, IPT_ERR_OVERFLOW when the device cannot hold this workspace (the caller retries with a smaller batch), or an error
-static int ensure_workspace(ipt_scene* s, size_t ray_cap, size_t hit_cap, size_t path_cap, bool two_hit_sets) {
-    Workspace& w = s->ws;
+static int ensure_workspace(ipt_scene* s, Workspace& w, size_t ray_cap, size_t hit_cap, size_t path_cap, bool two_hit_sets) {
     if (w.ray_cap >= ray_cap && w.hit_cap >= hit_cap && w.path_cap >= path_cap && (w.two_hit_sets || !two_hit_sets)) return IPT_OK;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream2));
     free_workspace(w);
     void** slots[8] = {(void**)&w.ray_o, (void**)&w.ray_d, (void**)&w.ray_x, (void**)&w.hit_a, (void**)&w.hit_b, (void**)&w.pathval, (void**)&w.hit_a2, (void**)&w.hit_b2};
     const size_t bytes[8] = {16 * ray_cap, 16 * ray_cap, 4 * ray_cap, 16 * std::max<size_t>(hit_cap, 1), 16 * std::max<size_t>(hit_cap, 1), 4 * path_cap,
@@ -1190,9 +1204,8 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     uint64_t budget = 24ull << 30;
     if (const char* e = std::getenv("IPT_QUEUE_BUDGET_GB")) { double gb = std::atof(e); if (gb > 0) budget = (uint64_t)(gb * (double)(1ull << 30)); }
     const uint64_t choice_key[5] = {batch, max_queued_w, max_hit_w, budget, fuse_next ? 1ull : 0ull};
-    if (s->ws.choice_batch && std::memcmp(choice_key, s->ws.choice_key, sizeof choice_key) == 0 &&
-        s->ws.ray_cap >= s->ws.choice_batch * max_queued_w && s->ws.hit_cap >= s->ws.choice_batch * max_hit_w && s->ws.path_cap >= s->ws.choice_batch) {
-        batch = s->ws.choice_batch; // same question as last time and the workspace it led to is still allocated
+    if (s->ws.choice_batch && s->ws.path_cap && std::memcmp(choice_key, s->ws.choice_key, sizeof choice_key) == 0) {
+        batch = s->ws.choice_batch; // same question as last time, and a workspace it led to is still allocated
     } else {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -1204,24 +1217,37 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     }
     const uint64_t batch_unclamped = batch;
     batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(total_paths, 1)));
+    // Mesh scenes keep TWO batches in flight, each on its own stream with its own queues (IPT_RENDER_LANES): a launch of the
+    // persistent traversal kernel ends with a tail — its longest rays, walked by a few lanes — during which the blocks of
+    // the other batch's launch move onto the idle SMs. A job that would fit one batch is split in two for that.
+    const bool two_lanes = IPT_RENDER_LANES == 2 && s->mesh && !s->smallpt && total_paths >= (1ull << 21);
+    if (two_lanes) batch = std::min<uint64_t>(batch, (total_paths + 1) / 2);
     if ((uint64_t)tw * th + batch > 0xFFFFFFFFull) return fail(IPT_ERR_UNSUPPORTED, "tile too large: tile pixels + batch must stay below 2^32");
+    bool alloc_halved = false;
     for (;;) {
-        int rc = ensure_workspace(s, batch * max_queued_w, batch * max_hit_w, batch, fuse_next);
+        int rc = ensure_workspace(s, s->ws, batch * max_queued_w, batch * max_hit_w, batch, fuse_next);
+        if (rc == IPT_OK && two_lanes) rc = ensure_workspace(s, s->ws2, batch * max_queued_w, batch * max_hit_w, batch, fuse_next);
         if (rc == IPT_OK) break;
         if (rc != IPT_ERR_OVERFLOW || batch <= 1024) return rc;
         batch >>= 1; // another tenant (torch, NCCL) took the memory between the query and the allocation
+        alloc_halved = true;
     }
-    if (batch == std::min<uint64_t>(batch_unclamped, std::max<uint64_t>(total_paths, 1)) && batch_unclamped <= total_paths) {
+    if (!alloc_halved) {
         std::memcpy(s->ws.choice_key, choice_key, sizeof choice_key);
         s->ws.choice_batch = batch_unclamped;
     }
 
     RenderCtx C;
     std::memset(&C, 0, sizeof C);
-    C.ray_o = s->ws.ray_o; C.ray_d = s->ws.ray_d; C.ray_x = s->ws.ray_x; C.pathval = s->ws.pathval;
-    C.hit_a[0] = s->ws.hit_a; C.hit_b[0] = s->ws.hit_b;
-    C.hit_a[1] = fuse_next ? s->ws.hit_a2 : s->ws.hit_a; C.hit_b[1] = fuse_next ? s->ws.hit_b2 : s->ws.hit_b;
-    C.cnt = s->d_cnt; C.fetch = s->d_cnt + (2 * IPT_MAX_DEPTH + 2); C.stats = s->d_stats;
+    auto use_lane = [&](int lane) { // the queues and counters of one lane
+        const Workspace& W = lane ? s->ws2 : s->ws;
+        C.ray_o = W.ray_o; C.ray_d = W.ray_d; C.ray_x = W.ray_x; C.pathval = W.pathval;
+        C.hit_a[0] = W.hit_a; C.hit_b[0] = W.hit_b;
+        C.hit_a[1] = fuse_next ? W.hit_a2 : W.hit_a; C.hit_b[1] = fuse_next ? W.hit_b2 : W.hit_b;
+        C.cnt = s->d_cnt + (size_t)lane * IPT_CNT_WORDS; C.fetch = C.cnt + (2 * IPT_MAX_DEPTH + 2);
+    };
+    use_lane(0);
+    C.stats = s->d_stats;
     C.sum = plane->sum; C.sumsq = plane->sumsq; C.count = plane->count;
     C.ray_cap = (uint32_t)std::min<size_t>(s->ws.ray_cap, 0xFFFFFFFFull); C.hit_cap = (uint32_t)std::min<size_t>(s->ws.hit_cap, 0xFFFFFFFFull);
     C.width = p->width; C.height = p->height;
@@ -1251,24 +1277,28 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
     uint32_t launches = 0;
     CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, sizeof(unsigned long long) * ST_COUNT, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev_begin, s->stream));
+    if (two_lanes) CUDA_TRY(cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
     size_t sm = stack_smem(s);
     const size_t msm = mesh_smem(s);
     uint32_t batches = 0;
     for (uint64_t g0 = 0; g0 < total_paths; g0 += batch, ++batches) {
+        const int lane = two_lanes ? (int)(batches & 1u) : 0;
+        cudaStream_t st = lane ? s->stream2 : s->stream;
+        use_lane(lane);
         C.g0 = g0;
         C.pass0 = p->pass_begin + (uint32_t)(g0 / C.tile_pixels);
         C.rem0 = (uint32_t)(g0 % C.tile_pixels);
         C.batch = (uint32_t)std::min<uint64_t>(batch, total_paths - g0);
-        CUDA_TRY(cudaMemsetAsync(s->d_cnt, 0, sizeof(uint32_t) * IPT_CNT_WORDS, s->stream));
+        CUDA_TRY(cudaMemsetAsync(C.cnt, 0, sizeof(uint32_t) * IPT_CNT_WORDS, st));
 #define TIMED(kind, LAUNCH)                                             \
     do {                                                                \
-        if (timing) { cudaEventRecord(ev_next(), s->stream); }         \
+        if (timing) { cudaEventRecord(ev_next(), st); }         \
         LAUNCH;                                                         \
         ++launches;                                                     \
-        if (timing) { cudaEventRecord(ev_next(), s->stream); ev_kind.push_back(kind); } \
+        if (timing) { cudaEventRecord(ev_next(), st); ev_kind.push_back(kind); } \
     } while (0)
         int gg = std::min<int>(s->grid_generate, (int)((C.batch + IPT_BLOCK - 1) / IPT_BLOCK));
-        TIMED(0, (k_generate<<<gg, IPT_BLOCK, 0, s->stream>>>(s->dev, C)));
+        TIMED(0, (k_generate<<<gg, IPT_BLOCK, 0, st>>>(s->dev, C)));
         bool traced = false; // the shade kernel of the previous depth has already traced the rays of this depth
         for (uint32_t d = 0; d < p->depth_max; ++d) {
             if (width_at[d] == 0) break;
@@ -1280,14 +1310,14 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
             if (persistent_mesh) {
                 // mesh scenes: persistent warps that refill idle lanes from the ray queue (ipt_trace.cuh)
                 if (last) {
-                    if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<true, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
-                    else TIMED(1, (k_extend_mesh<true><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
+                    if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<true, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, msm, st>>>(s->dev, C, d)));
+                    else TIMED(1, (k_extend_mesh<true><<<std::max(1, std::min(s->grid_mesh_last, cap_blocks)), IPT_BLOCK, msm, st>>>(s->dev, C, d)));
                     break;
                 }
-                if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<false, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
-                else TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, msm, s->stream>>>(s->dev, C, d)));
+                if (s->mesh_box_scene) TIMED(1, (k_extend_mesh<false, SPEC_BOX_SCENE><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, msm, st>>>(s->dev, C, d)));
+                else TIMED(1, (k_extend_mesh<false><<<std::max(1, std::min(s->grid_mesh, cap_blocks)), IPT_BLOCK, msm, st>>>(s->dev, C, d)));
                 int gs2 = std::max(1, std::min(s->grid_shade, cap_blocks));
-                TIMED(2, (k_shade<FUSE_NONE, false><<<gs2, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                TIMED(2, (k_shade<FUSE_NONE, false><<<gs2, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
                 continue;
             }
             // camera rays are traced with the reference's exact arithmetic; rays downstream of a random number with the
@@ -1297,16 +1327,16 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
                 if (last) {
                     int g = std::max(1, std::min(s->grid_extend_last, cap_blocks));
 #define CALL(SP, MS)                                                                                             \
-    if (MS || exact_d) TIMED(1, (k_extend<SP, MS, true, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d))); \
-    else TIMED(1, (k_extend<SP, false, true, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
+    if (MS || exact_d) TIMED(1, (k_extend<SP, MS, true, true><<<g, IPT_BLOCK, sm, st>>>(s->dev, C, d))); \
+    else TIMED(1, (k_extend<SP, false, true, false><<<g, IPT_BLOCK, sm, st>>>(s->dev, C, d)))
                     DISPATCH_SM(s, CALL);
 #undef CALL
                     break;
                 }
                 int g = std::max(1, std::min(s->grid_extend, cap_blocks));
 #define CALL(SP, MS)                                                                                              \
-    if (MS || exact_d) TIMED(1, (k_extend<SP, MS, false, true><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d))); \
-    else TIMED(1, (k_extend<SP, false, false, false><<<g, IPT_BLOCK, sm, s->stream>>>(s->dev, C, d)))
+    if (MS || exact_d) TIMED(1, (k_extend<SP, MS, false, true><<<g, IPT_BLOCK, sm, st>>>(s->dev, C, d))); \
+    else TIMED(1, (k_extend<SP, false, false, false><<<g, IPT_BLOCK, sm, st>>>(s->dev, C, d)))
                 DISPATCH_SM(s, CALL);
 #undef CALL
             }
@@ -1316,34 +1346,38 @@ int ipt_render(ipt_scene* s, ipt_plane* plane, const ipt_render_params* p, ipt_r
             bool child_last = width_at[d + 1] != 0 && ((d + 2 == p->depth_max) || p->schedule[d + 1] == 0);
             if (child_last && fuse_last) {
                 int gf = std::max(1, std::min(s->grid_shade_fused, cap_blocks));
-                if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_LIGHT_BVH><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light && s->geom_fast && s->all_lambert) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_LAMBERT_BOX><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_BOX_SCENE><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_AREA_LIGHT><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_LIGHT><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else TIMED(2, (k_shade<FUSE_LAST, false, SPEC_FEW_LIGHTS><<<gf, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                if (s->smallpt) TIMED(2, (k_shade<FUSE_LAST, true><<<gf, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_LIGHT_BVH><<<gf, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast && s->all_lambert) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_LAMBERT_BOX><<<gf, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_BOX_SCENE><<<gf, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_AREA_LIGHT><<<gf, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_LAST, false, SPEC_ONE_LIGHT><<<gf, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_LAST, false, SPEC_FEW_LIGHTS><<<gf, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
                 break;
             }
             if (fuse_next && width_at[d + 1] != 0) {
                 int gn = std::max(1, std::min(s->grid_shade_next, cap_blocks));
-                if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_LIGHT_BVH><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light && s->geom_fast && s->all_lambert) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_LAMBERT_BOX><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_BOX_SCENE><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_AREA_LIGHT><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_LIGHT><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
-                else TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_FEW_LIGHTS><<<gn, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+                if (s->smallpt) TIMED(2, (k_shade<FUSE_NEXT, true><<<gn, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->dev.n_light_bvh) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_LIGHT_BVH><<<gn, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast && s->all_lambert) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_LAMBERT_BOX><<<gn, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->inline_area_light && s->geom_fast) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_BOX_SCENE><<<gn, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->inline_area_light) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_AREA_LIGHT><<<gn, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else if (s->dev.light_inline) TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_ONE_LIGHT><<<gn, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
+                else TIMED(2, (k_shade<FUSE_NEXT, false, SPEC_FEW_LIGHTS><<<gn, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
                 traced = true; // the rays of depth d+1 are traced by this launch: no k_extend for them
                 continue;
             }
             int gs = std::max(1, std::min(s->grid_shade, cap_blocks));
-            if (s->smallpt) TIMED(2, (k_shade<FUSE_NONE, true><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d))); // reference-order sampling (ipt_shading.cuh)
-            else TIMED(2, (k_shade<FUSE_NONE, false><<<gs, IPT_BLOCK, 0, s->stream>>>(s->dev, C, d)));
+            if (s->smallpt) TIMED(2, (k_shade<FUSE_NONE, true><<<gs, IPT_BLOCK, 0, st>>>(s->dev, C, d))); // reference-order sampling (ipt_shading.cuh)
+            else TIMED(2, (k_shade<FUSE_NONE, false><<<gs, IPT_BLOCK, 0, st>>>(s->dev, C, d)));
         }
-        TIMED(3, (k_accumulate<<<std::max(1, gg), IPT_BLOCK, 0, s->stream>>>(C)));
+        TIMED(3, (k_accumulate<<<std::max(1, gg), IPT_BLOCK, 0, st>>>(C)));
 #undef TIMED
         CUDA_TRY(cudaGetLastError());
+    }
+    if (two_lanes) {
+        CUDA_TRY(cudaEventRecord(s->ev_join, s->stream2));
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
     }
     CUDA_TRY(cudaEventRecord(s->ev_end, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));

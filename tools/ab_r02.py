@@ -17,6 +17,7 @@ VARIANTS = {
     "lightq": ["IPT_LIGHT_QNODES=1"],      # light LBVH through its 32-byte quantised nodes (measured: no gain)
     "nosamp": ["IPT_LIGHT_SAMP_RECORDS=0"], # light sampling from the 112-byte records
     "walls": ["IPT_SHADOW_SKIP_WALLS=0"],  # shadow rays of box scenes test the wall planes too
+    "twolanes": ["IPT_RENDER_LANES=2"],   # mesh scenes: two batches in flight on two streams (measured: +2-4 % at best)
     "meshv1": ["IPT_MESH_POOLS=0"],        # the round-1 mesh traversal kernel (no ready / done pools)
     "bounds": ["IPT_DEBUG_BOUNDS"],        # every queue append checked against its capacity (compute-sanitizer is closed on this pool)
 }
