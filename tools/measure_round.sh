@@ -10,14 +10,14 @@ timeout 1500 python -m pytest tests -m gpu -q -s --durations=8 > gpurun_out/pyte
 grep -hE "IMAGE_STATS|C3_CRN|CRN_FULL|FAILED|^E  " gpurun_out/pytest_$TAG.log | cut -c1-330 > gpurun_out/pytest_${TAG}_stats.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
-for w in c2:2 c3:4 c5:1; do
+for w in c2:2 c3:16 c5:1; do
   n=${w%%:*}; p=${w##*:}
   timeout 120 python tools/profile_run.py $n $p > gpurun_out/plain_$n.log 2>&1 && \
   timeout 600 ncu --metrics $M --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}_$n.csv python tools/profile_run.py $n $p > gpurun_out/ncu_l_$n.log 2>&1
   cat gpurun_out/plain_$n.log
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 4 -c 2 -o gpurun_out/prof_${TAG}_c2 python tools/profile_run.py c2 2 > gpurun_out/ncu_f_c2.log 2>&1; tail -1 gpurun_out/ncu_f_c2.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_extend_mesh -s 8 -c 2 -o gpurun_out/prof_${TAG}_c3 python tools/profile_run.py c3 4 > gpurun_out/ncu_f_c3.log 2>&1; tail -1 gpurun_out/ncu_f_c3.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_extend_mesh -s 8 -c 2 -o gpurun_out/prof_${TAG}_c3 python tools/profile_run.py c3 16 > gpurun_out/ncu_f_c3.log 2>&1; tail -1 gpurun_out/ncu_f_c3.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 4 -c 2 -o gpurun_out/prof_${TAG}_c5 python tools/profile_run.py c5 1 > gpurun_out/ncu_f_c5.log 2>&1; tail -1 gpurun_out/ncu_f_c5.log
 for n in c2 c3 c5; do
   ncu -i gpurun_out/prof_${TAG}_$n.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_${n}_raw.csv 2>/dev/null
