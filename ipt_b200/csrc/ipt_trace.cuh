@@ -242,16 +242,12 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 #ifndef IPT_MESH_MIN_BLOCKS
 #define IPT_MESH_MIN_BLOCKS 4
 #endif
-#ifndef IPT_MESH_POOLS
-#define IPT_MESH_POOLS 1 // 0: the round-1 kernel (setup and finalisation by whichever lanes happen to be idle / finished; tuning A/B only)
-#endif
 #define IPT_POOL 64 // entries per warp and pool: fewer than 32 wait when up to 32 more arrive
 // dynamic shared memory of k_extend_mesh: the short stacks, then per warp a READY pool (ray index, analytic hit distance,
 // analytic primitive) and a DONE pool (ray index, hit distance, primitive id, primitive id as queued)
 #define IPT_MESH_POOL_WORDS (7 * IPT_POOL)
-#define IPT_MESH_SMEM_BYTES ((IPT_STACK_SHORT * IPT_BLOCK + (IPT_MESH_POOLS ? (IPT_BLOCK / 32) * IPT_MESH_POOL_WORDS : 0)) * sizeof(uint32_t))
+#define IPT_MESH_SMEM_BYTES ((IPT_STACK_SHORT * IPT_BLOCK + (IPT_BLOCK / 32) * IPT_MESH_POOL_WORDS) * sizeof(uint32_t))
 
-#if IPT_MESH_POOLS
 // SPEC (see SceneSpec in ipt_kernels.cuh): SPEC_BOX_SCENE = one inline area light, analytic part = grouped box planes +
 // inline spheres — the kernel then carries no light-LBVH walk (and not its local stack), no sphere-light code and none of
 // the generic primitive scans; SPEC_RUNTIME decides everything from the scene.
@@ -265,8 +261,8 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 //             takes the next ray at once;
 //   finalise  whenever 32 results wait, the warp runs the light test / decision / emission / hit append of main.cpp:111-128
 //             for them.
-// The round-1 kernel ran setup and finalisation on the 4-8 lanes that happened to be idle or finished (16 of 32 lanes per
-// instruction overall, profiles/ncu_r02_k_extend_mesh_*); the arithmetic per ray is unchanged.
+// Round 1's kernel ran setup and finalisation on the 4-8 lanes that happened to be idle or finished (profiles/tuning_r02.md:
+// c3_tree +8.7 % for the pools); the arithmetic per ray is unchanged.
 template <bool LAST, int SPEC = SPEC_RUNTIME>
 __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
     const uint32_t n = C.cnt[2 * depth];
@@ -514,209 +510,5 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
     flush_stat(C.stats, ST_LIGHTS, tc.lights);
     flush_stat(C.stats, ST_LIGHT_NODES, tc.light_nodes);
 }
-#else
-// SPEC (see SceneSpec in ipt_kernels.cuh): SPEC_BOX_SCENE = one inline area light, analytic part = grouped box planes +
-// inline spheres — the kernel then carries no light-LBVH walk (and not its 64-entry local stack), no sphere-light code
-// and none of the generic primitive scans; SPEC_RUNTIME decides everything from the scene.
-template <bool LAST, int SPEC = SPEC_RUNTIME>
-__global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(const __grid_constant__ DevScene S, const __grid_constant__ RenderCtx C, uint32_t depth) {
-    const uint32_t n = C.cnt[2 * depth];
-    uint32_t* next = &C.fetch[depth];
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t n_surface = 0, n_light = 0, n_miss = 0, n_dropped = 0;
-    TraceCounters tc{0, 0, 0, 0};
-    bool have = false, trav = false, exhausted = false;
-    float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
-    GridRay R;
-    R.inv = mk3(0, 0, 0); R.c = mk3(0, 0, 0);
-    f3 lpos = mk3(0, 0, 0);
-    float a_t = IPT_INF, best_t = IPT_INF, sv = -1.0f, ldist = 0.0f;
-    uint32_t a_prim = IPT_NO_HIT, best_orig = IPT_NO_HIT, best_pos = IPT_NO_HIT, lwhich = IPT_NO_HIT, node = 0, pend = IPT_NO_HIT;
-    TravStack st;
-    st.sm = ipt_dyn_smem + threadIdx.x;
-    st.n = 0;
-    while (true) {
-        // ---- replenish idle lanes
-        uint32_t idle = __ballot_sync(0xffffffffu, !have);
-        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= IPT_REFILL_MIN)) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + __popc(idle) >= n) exhausted = true;
-            uint32_t i = base + __popc(idle & lt_mask);
-            if (!have && i < n) {
-                ro = C.ray_o[i];
-                rd = C.ray_d[i];
-                sv = C.ray_x[i];
-                f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
-                bool go = true;
-                if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) { // shadow ray: nothing to do unless a light lies along it
-                    lwhich = IPT_NO_HIT;
-                    float lpdf;
-                    if (lights_inline<SPEC>(S)) {
-                        go = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc); // density from lpos when the ray is finalised
-                    } else {
-                        go = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc);
-                        ro.w = resolve_weight(S, ro.w, sv, lpdf); // resolved now: no density register lives through the traversal
-                        sv = -1.0f;
-                    }
-                }
-                if (go) {
-                    double dd = (double)IPT_INF;
-                    a_t = IPT_INF; a_prim = IPT_NO_HIT;
-                    analytic_closest<false, IPT_SPEC_FAST_GEOMETRY(SPEC)>(S, o, d, dd, a_t, a_prim);
-                    best_t = a_t; best_orig = IPT_NO_HIT; best_pos = IPT_NO_HIT;
-                    have = true;
-                    if (S.n_tris == 1) {
-                        test_triangle(S, 0, o, d, best_t, best_orig, best_pos, false, tc);
-                        trav = false;
-                    } else {
-                        R = grid_ray(S.grid, o, d);
-                        node = 0; pend = IPT_NO_HIT; st.n = 0; trav = true;
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, have) == 0) {
-            if (exhausted) break;
-            continue;
-        }
-        // ---- a few BVH node visits. Triangle tests are POSTPONED (speculative while-while traversal, Aila & Laine
-        // 2009): a hit leaf is parked in `pend` (further ones go on the stack) and lanes keep walking inner nodes;
-        // the exact triangle test then runs for many lanes at once instead of for the 1-2 lanes that happen to
-        // reach a leaf in the same step.
-        for (int step = 0; step < IPT_TRAV_STEPS; ++step) {
-            if (have && trav) {
-                if (node != IPT_NO_HIT && pend == IPT_NO_HIT) {
-#if IPT_BVH_WIDE_NODES
-                    f8 n0 = ldg256(&S.nodes[node]);
-                    f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
-                    ++tc.nodes;
-                    uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
-                    float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], R.c, R.inv, best_t);
-                    float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], R.c, R.inv, best_t);
-#else
-                    u8x32 q = ldg256u(&S.qnodes[node]);
-                    ++tc.nodes;
-                    uint32_t left = q.v[6], right = q.v[7];
-                    float tn0 = slab_q(q.v[0], q.v[1], q.v[2], R, best_t);
-                    float tn1 = slab_q(q.v[3], q.v[4], q.v[5], R, best_t);
-#endif
-                    bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
-                    if (h0 && (left & 0x80000000u)) { pend = left; h0 = false; }
-                    if (h1 && (right & 0x80000000u)) {
-                        if (pend == IPT_NO_HIT) pend = right; else st.push(right);
-                        h1 = false;
-                    }
-                    uint32_t nxt = IPT_NO_HIT;
-                    if (h0 && h1) {
-                        bool first0 = tn0 <= tn1;
-                        nxt = first0 ? left : right;
-                        st.push(first0 ? right : left);
-                    } else if (h0) nxt = left;
-                    else if (h1) nxt = right;
-                    node = nxt;
-                }
-                if (node == IPT_NO_HIT && pend == IPT_NO_HIT) {
-                    if (st.n == 0) trav = false;
-                    else {
-                        uint32_t x = st.pop();
-                        if (x & 0x80000000u) pend = x; else node = x;
-                    }
-                }
-            }
-            uint32_t pm = __ballot_sync(0xffffffffu, have && trav && pend != IPT_NO_HIT);
-            uint32_t walk = __ballot_sync(0xffffffffu, have && trav && pend == IPT_NO_HIT);
-            if (pm && (__popc(pm) >= IPT_LEAF_BATCH || walk == 0 || step == IPT_TRAV_STEPS - 1)) {
-                if (have && trav && pend != IPT_NO_HIT) {
-                    test_triangle(S, pend & 0x7FFFFFFFu, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), best_t, best_orig, best_pos, best_orig != IPT_NO_HIT, tc);
-                    pend = IPT_NO_HIT;
-                    if (node == IPT_NO_HIT && st.n == 0) trav = false;
-                }
-            }
-            if (!__any_sync(0xffffffffu, have && trav)) break;
-        }
-        // ---- finalise finished rays (main.cpp:111-128), compact the survivors
-        bool fin = have && !trav;
-        bool emit = false;
-        uint32_t prim = IPT_NO_HIT, iprim = IPT_NO_HIT;
-        float t = IPT_INF;
-        if (fin) {
-            f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
-            bool tri = best_orig != IPT_NO_HIT;
-            prim = tri ? S.n_prims + best_orig : a_prim;
-            iprim = tri ? S.n_prims + best_pos : a_prim;
-            t = tri ? best_t : a_t;
-            bool lh;
-            float lpdf = 0.0f;
-            if (LAST && !(C.flags & IPT_FLAG_RESOLVE_LAST_LEVEL)) lh = true;
-            else {
-                lwhich = IPT_NO_HIT;
-                if (lights_inline<SPEC>(S)) lh = trace_lights<false, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc);
-                else lh = trace_lights<true, SPEC>(S, o, d, lwhich, lpos, lpdf, ldist, tc);
-            }
-            // single inline light: its density follows from the hit position that is kept anyway
-            if (lights_inline<SPEC>(S) && lh && S.n_lights) lpdf = S.lights[0].weight * light_pdf_at<IPT_SPEC_AREA_LIGHTS(SPEC)>(S.lights[0], o, lpos);
-            bool sh = prim != IPT_NO_HIT;
-#ifdef IPT_DEBUG_PRINT
-            float K = ro.w;
-#endif
-            ro.w = resolve_weight(S, ro.w, sv, lpdf);
-#ifdef IPT_DEBUG_PRINT
-            if (C.flags & IPT_FLAG_DEBUG_PRINT)
-                printf("GPU mesh extend d=%u o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) K=%.9g sv=%.9g thr=%.9g lh=%d lpos=(%.9g %.9g %.9g) prim=%u t=%.9g\n", depth, o.x, o.y, o.z,
-                       d.x, d.y, d.z, K, sv, ro.w, (int)lh, lpos.x, lpos.y, lpos.z, prim, t);
-#endif
-            if (!isfinite(ro.w)) {
-                ++n_dropped; // non-finite multiplier (main.cpp:175): drop this sample
-            } else {
-                bool light_wins = false;
-                if (lh) {
-                    float len_surf = sh ? xlength3(xsub3(xpoint(o, d, t), o)) : IPT_INF;
-                    light_wins = !sh || len_surf > ldist; // main.cpp:113 (ldist = length(light position - origin))
-                }
-                if (light_wins) {
-                    ++n_light;
-                    float power = light_power<SPEC>(S, lwhich);
-                    atomicAdd(&C.pathval[__float_as_uint(rd.w) & C.slot_mask], ro.w * power);
-                } else if (sh) {
-                    ++n_surface;
-                    emit = !LAST;
-                } else {
-                    ++n_miss;
-                }
-            }
-            have = false;
-        }
-        if (!LAST) {
-            uint32_t ballot = __ballot_sync(0xffffffffu, emit);
-            if (ballot) {
-                uint32_t basepos = 0;
-                if (lane == 0) basepos = atomicAdd(&C.cnt[2 * depth + 1], (uint32_t)__popc(ballot));
-                basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                if (emit) {
-                    uint32_t j = basepos + __popc(ballot & lt_mask);
-                    f3 p = xpoint(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), t);
-                    float2 oct = oct_encode(mk3(rd.x, rd.y, rd.z));
-                    if (IPT_BOUNDS_OK(j, C.hit_cap, C.stats)) {
-                        C.hit_a[depth & 1][j] = make_float4(p.x, p.y, p.z, ro.w);
-                        C.hit_b[depth & 1][j] = make_uint4(__float_as_uint(rd.w), iprim, __float_as_uint(oct.x), __float_as_uint(oct.y));
-                    }
-                }
-            }
-        }
-    }
-    flush_stat(C.stats, ST_SURFACE, n_surface);
-    flush_stat(C.stats, ST_LIGHT, n_light);
-    flush_stat(C.stats, ST_MISS, n_miss);
-    flush_stat(C.stats, ST_DROPPED, n_dropped);
-    flush_stat(C.stats, ST_NODES, tc.nodes);
-    flush_stat(C.stats, ST_TRIS, tc.tris);
-    flush_stat(C.stats, ST_LIGHTS, tc.lights);
-    flush_stat(C.stats, ST_LIGHT_NODES, tc.light_nodes);
-}
-
-#endif // IPT_MESH_POOLS
 
 } // namespace iptd
