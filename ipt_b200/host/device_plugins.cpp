@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <thread>
@@ -374,6 +375,14 @@ ipt_plane* DevicePlane::attach(const std::shared_ptr<DeviceContext>& ctx) {
     if (carry) check(ipt_plane_upload(plane_, s.data(), q.data(), c.data()));
     return plane_;
 }
+void DevicePlane::clear() {
+    if (plane_) check(ipt_plane_clear(plane_));
+}
+void DevicePlane::upload(const std::vector<float>& sum, const std::vector<float>& sumsq, const std::vector<uint32_t>& count) {
+    if (sum.size() != width * height || sumsq.size() != sum.size() || count.size() != sum.size()) throw Error(IPT_ERR_INVALID, "DevicePlane::upload: array sizes do not match the plane");
+    if (!plane_) attach(std::make_shared<DeviceContext>(SceneBuilder())); // the next render carries the accumulators over to its scene
+    check(ipt_plane_upload(plane_, sum.data(), sumsq.data(), count.data()));
+}
 void DevicePlane::addRay(float x, float y, float value) {
     if (!plane_) attach(std::make_shared<DeviceContext>(SceneBuilder()));
     check(ipt_plane_add_rays(plane_, plane_mode, 1, &x, &y, &value));
@@ -605,6 +614,104 @@ ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const i
 #endif
     flush_foreign(r_plane, p, sum, count);
     return stats;
+}
+
+
+// ---- ProgressiveSession ---------------------------------------------------------------------------------------
+ProgressiveSession::ProgressiveSession(Scene scene, size_t width, size_t height, uint32_t passes_per_call, std::vector<int> devices)
+    : scene_(std::move(scene)), plane_(width, height), devices_(std::move(devices)), passes_per_call_(passes_per_call ? passes_per_call : 1) {
+    ipt_render_params_default(&params);
+    params.width = (uint32_t)width;
+    params.height = (uint32_t)height;
+    plane_.plane_mode = IPT_PLANE_GUI; // the interactive window's cell mapping (Gui::addRay, gui.cpp:168-172)
+}
+uint64_t ProgressiveSession::step(unsigned calls) {
+    for (unsigned c = 0; c < calls; ++c) {
+        ipt_render_params p = params;
+        if (next_pass_ + passes_per_call_ > 0xFFFFFFFFull) throw Error(IPT_ERR_UNSUPPORTED, "ProgressiveSession: pass counter exhausted");
+        p.pass_begin = (uint32_t)next_pass_;
+        p.pass_count = passes_per_call_;
+        ipt_render_stats st = render_sample(scene_, plane_, p, devices_);
+        next_pass_ += passes_per_call_;
+        rays_ += st.rays;
+    }
+    return samples_per_pixel();
+}
+void ProgressiveSession::resetImage() { // pass numbers keep growing: the new image draws fresh random streams
+    plane_.clear();
+    first_pass_ = next_pass_;
+}
+void ProgressiveSession::key(int key) {
+    DeviceCamera* cam = dynamic_cast<DeviceCamera*>(const_cast<Camera*>(scene_.camera.get()));
+    if (!cam) throw Error(IPT_ERR_UNSUPPORTED, "ProgressiveSession::key: the scene's camera is not a DeviceCamera");
+    cam->orbit(key);
+    resetImage();
+}
+void ProgressiveSession::wheel(int clicks) { // glare_cutoff *= pow(sqrt(2.0f), wheel): float sqrt, double pow and product (gui.cpp:142)
+    glare_cutoff = (float)((double)glare_cutoff * std::pow((double)std::sqrt(2.0f), clicks));
+}
+
+namespace {
+struct CheckpointHeader { // little-endian, fixed layout; followed by sum[n], sumsq[n] (float) and count[n] (uint32)
+    char magic[8];
+    uint32_t width, height, depth_max, plane_mode, passes_per_call, schedule[IPT_MAX_DEPTH];
+    uint64_t seed, next_pass, first_pass, rays;
+    float glare_cutoff, camera[12];
+    uint32_t has_camera, reserved;
+};
+const char kCheckpointMagic[8] = {'I', 'P', 'T', 'C', 'K', 'P', 'T', '1'};
+} // namespace
+
+void ProgressiveSession::checkpoint(const std::string& path) {
+    CheckpointHeader h{};
+    std::memcpy(h.magic, kCheckpointMagic, 8);
+    h.width = params.width; h.height = params.height; h.depth_max = params.depth_max; h.plane_mode = plane_.plane_mode;
+    h.passes_per_call = passes_per_call_;
+    std::memcpy(h.schedule, params.schedule, sizeof h.schedule);
+    h.seed = params.seed; h.next_pass = next_pass_; h.first_pass = first_pass_; h.rays = rays_;
+    h.glare_cutoff = glare_cutoff;
+    if (const DeviceCamera* cam = dynamic_cast<const DeviceCamera*>(scene_.camera.get())) {
+        const glm::vec3* v[4] = {&cam->position, &cam->direction, &cam->right, &cam->up};
+        for (int k = 0; k < 4; ++k) { h.camera[3 * k] = v[k]->x; h.camera[3 * k + 1] = v[k]->y; h.camera[3 * k + 2] = v[k]->z; }
+        h.has_camera = 1;
+    }
+    std::vector<float> sum, sumsq;
+    std::vector<uint32_t> count;
+    plane_.sums(sum, sumsq, count);
+    const std::string tmp = path + ".tmp";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) throw Error(IPT_ERR_INVALID, "ProgressiveSession::checkpoint: cannot write " + tmp);
+    bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(sum.data(), 4, sum.size(), f) == sum.size() &&
+              std::fwrite(sumsq.data(), 4, sumsq.size(), f) == sumsq.size() && std::fwrite(count.data(), 4, count.size(), f) == count.size();
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) { std::remove(tmp.c_str()); throw Error(IPT_ERR_INVALID, "ProgressiveSession::checkpoint: write to " + path + " failed"); }
+}
+bool ProgressiveSession::resume(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    CheckpointHeader h{};
+    const size_t n = (size_t)params.width * params.height;
+    std::vector<float> sum(n), sumsq(n);
+    std::vector<uint32_t> count(n);
+    bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, kCheckpointMagic, 8) == 0;
+    // a checkpoint belongs to one estimator and one frame: resuming it under other parameters would mix two images
+    const bool same = ok && h.width == params.width && h.height == params.height && h.depth_max == params.depth_max &&
+                      h.plane_mode == plane_.plane_mode && h.passes_per_call == passes_per_call_ &&
+                      std::memcmp(h.schedule, params.schedule, sizeof h.schedule) == 0;
+    if (same) ok = std::fread(sum.data(), 4, n, f) == n && std::fread(sumsq.data(), 4, n, f) == n && std::fread(count.data(), 4, n, f) == n;
+    std::fclose(f);
+    if (!ok) throw Error(IPT_ERR_INVALID, "ProgressiveSession::resume: " + path + " is not a complete ipt_b200 checkpoint");
+    if (!same) throw Error(IPT_ERR_INVALID, "ProgressiveSession::resume: " + path + " was written for another frame size, depth, split schedule, plane mode or step size");
+    params.seed = h.seed;
+    next_pass_ = h.next_pass; first_pass_ = h.first_pass; rays_ = h.rays;
+    glare_cutoff = h.glare_cutoff;
+    if (h.has_camera)
+        if (DeviceCamera* cam = dynamic_cast<DeviceCamera*>(const_cast<Camera*>(scene_.camera.get()))) {
+            cam->position = glm::vec3(h.camera[0], h.camera[1], h.camera[2]); cam->direction = glm::vec3(h.camera[3], h.camera[4], h.camera[5]);
+            cam->right = glm::vec3(h.camera[6], h.camera[7], h.camera[8]); cam->up = glm::vec3(h.camera[9], h.camera[10], h.camera[11]);
+        }
+    plane_.upload(sum, sumsq, count);
+    return true;
 }
 
 } // namespace ipt_b200

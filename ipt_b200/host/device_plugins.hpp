@@ -149,6 +149,9 @@ public:
     std::vector<float> display(float glare_cutoff = 1.01f);
     void save(const char* path);
 
+    void clear();                                        // Gui::resetImage (gui.cpp:152-160): accumulators back to zero
+    void upload(const std::vector<float>& sum, const std::vector<float>& sumsq, const std::vector<uint32_t>& count); // resume
+
     // used by render_sample: (re)attach to the device context of the scene being rendered
     ipt_plane* attach(const std::shared_ptr<DeviceContext>& ctx);
 
@@ -187,5 +190,38 @@ ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const i
 // frame on its own replica of the scene; the per-device accumulators are merged into the plane of devices[0] with
 // ipt_plane_merge (peer copy + add on the device). The result equals the single-device render of the same passes.
 ipt_render_stats render_sample(const Scene& scene, RenderPlane& r_plane, const ipt_render_params& params, const std::vector<int>& devices);
+
+
+// ---- the caller side of the interactive loop, headless -----------------------------------------
+// src/main.cpp:258-269   the render threads call render_sample(scene, *gui, stats) forever: one more sample per pixel per call
+// src/gui.cpp:105-137    arrow keys orbit / dolly the camera, then resetImage() + updateDisplay()
+// src/gui.cpp:141-145    the mouse wheel scales glare_cutoff by sqrt(2) per click
+// src/gui.cpp:83-87      updateDisplay(): normalize(glare(image, glare_cutoff));   :192-194 save()
+// plus what the reference lacks: accumulator checkpoints. The Philox counters carry the pass index, so a session resumed
+// from a checkpoint continues the very image the uninterrupted session would have produced.
+class ProgressiveSession {
+public:
+    ipt_render_params params;   // depth_max, split schedule, seed, plane mode: set before the first step()
+    float glare_cutoff = 1.01f; // gui.h:24
+    ProgressiveSession(Scene scene, size_t width, size_t height, uint32_t passes_per_call = 4, std::vector<int> devices = {0});
+    uint64_t step(unsigned calls = 1); // `calls` x passes_per_call more samples per pixel; returns samples per pixel of the image
+    void key(int key);                 // IPT_KEY_*: the camera moves, the image restarts (the scene's camera must be a DeviceCamera)
+    void resetImage();
+    void wheel(int clicks);
+    std::vector<float> display() { return plane_.display(glare_cutoff); }
+    void save(const char* path) { plane_.save(path); }
+    void checkpoint(const std::string& path); // atomic: written next to `path`, then renamed over it
+    bool resume(const std::string& path);     // false: no such file. Throws when the file belongs to another estimator / frame
+    uint64_t samples_per_pixel() const { return next_pass_ - first_pass_; }
+    uint64_t rays() const { return rays_; }
+    DevicePlane& plane() { return plane_; }
+
+private:
+    Scene scene_;
+    DevicePlane plane_;
+    std::vector<int> devices_;
+    uint32_t passes_per_call_;
+    uint64_t next_pass_ = 0, first_pass_ = 0, rays_ = 0;
+};
 
 } // namespace ipt_b200

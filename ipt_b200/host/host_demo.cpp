@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 // a RenderPlane the library knows nothing about: GridRenderPlane::addRay's arithmetic (src/GridRenderPlane.cpp:61-75)
 struct ForeignGridPlane : public RenderPlane {
@@ -82,6 +83,42 @@ int main(int argc, char** argv) {
         cam->orbit(IPT_KEY_RIGHT);
         float orbit_err = std::fabs(cam->position.x - before.x) + std::fabs(cam->position.y - before.y) + std::fabs(cam->position.z - before.z);
         dplane.addRay(0.5f, 0.5f, 1.0f);
+        // the interactive loop, headless, with a checkpoint in the middle: A renders 2 + 2 calls, B resumes A's checkpoint after
+        // the first 2 and renders the other 2 — the same image (counters equal, sums equal up to the order of the float atomics);
+        // then a key restarts the image and the wheel scales the glare cutoff like Gui::work does
+        size_t session_counters_equal = 0, session_spp_a = 0, session_spp_b = 0, session_spp_after_key = 0;
+        double session_max_rel = 0;
+        float session_cutoff = 0;
+        int session_refused = 0;
+        if (argc > 3) {
+            const std::string ckpt = std::string(argv[3]) + ".ckpt";
+            ipt_b200::ProgressiveSession a(ipt_b200::make_scene(name), 64, 64, 2);
+            a.step(2);
+            a.checkpoint(ckpt);
+            session_spp_a = a.step(2);
+            ipt_b200::ProgressiveSession b(ipt_b200::make_scene(name), 64, 64, 2);
+            if (!b.resume(ckpt)) throw ipt_b200::Error(IPT_ERR_INVALID, "checkpoint not found");
+            session_spp_b = b.step(2);
+            std::vector<float> sa, qa, sb, qb;
+            std::vector<uint32_t> ca, cb;
+            a.plane().sums(sa, qa, ca);
+            b.plane().sums(sb, qb, cb);
+            for (size_t i = 0; i < ca.size(); ++i) {
+                session_counters_equal += ca[i] == cb[i];
+                double scale = std::fabs(sa[i]) > 1e-6 ? std::fabs(sa[i]) : 1e-6;
+                double rel = std::fabs((double)sa[i] - sb[i]) / scale;
+                if (rel > session_max_rel) session_max_rel = rel;
+            }
+            ipt_b200::ProgressiveSession c(ipt_b200::make_scene(name), 64, 64, 3); // another step size: not the same estimator run
+            try { c.resume(ckpt); } catch (const ipt_b200::Error&) { session_refused = 1; }
+            b.key(IPT_KEY_LEFT);
+            session_spp_after_key = b.step(1);
+            b.wheel(2);
+            session_cutoff = b.glare_cutoff;
+            std::remove(ckpt.c_str());
+        }
+        printf("{\"session_counters_equal\": %zu, \"session_max_rel\": %.3g, \"session_spp\": [%zu, %zu, %zu], \"session_cutoff\": %.9g, \"session_refused\": %d}\n",
+               session_counters_equal, session_max_rel, session_spp_a, session_spp_b, session_spp_after_key, session_cutoff, session_refused);
         printf("{\"display_max\": %.9g, \"orbit_round_trip_error\": %.9g}\n", shown_max, orbit_err);
         printf("{\"scene\": \"%s\", \"paths\": %llu, \"rays\": %llu, \"mean_device_plane\": %.9g, \"count_device_plane\": %zu, "
                "\"mean_foreign_plane\": %.9g, \"cells_foreign_plane\": %zu, \"hit\": %d, \"hit_pos\": [%.9g, %.9g, %.9g], "

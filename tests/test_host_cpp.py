@@ -42,8 +42,11 @@ def test_render_sample_through_the_cpp_interfaces(scene, host_demo, oracle, tmp_
     png = tmp_path / "result.png"
     r = subprocess.run([str(host_demo), scene, "4", str(png)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    multi, first, last = r.stdout.strip().splitlines()
+    multi, session, first, last = r.stdout.strip().splitlines()
     multi = json.loads(multi)   # ipt_b200::render_sample(scene, plane, params, devices): same passes on two device slots
+    session = json.loads(session)  # ipt_b200::ProgressiveSession: the interactive loop headless, checkpoint / resume in C++
+    assert session["session_spp"] == [8, 8, 2] and session["session_counters_equal"] == 64 * 64 and session["session_max_rel"] < 2e-5
+    assert session["session_refused"] == 1 and abs(session["session_cutoff"] - 1.01 * 2.0) < 1e-5   # wheel: sqrt(2)^2
     stage = json.loads(first)
     assert stage["display_max"] == 1.0 and stage["orbit_round_trip_error"] < 1e-5   # DevicePlane::display, DeviceCamera::orbit
     from test_output_host import decode_png_gray8
