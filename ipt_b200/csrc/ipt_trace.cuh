@@ -235,6 +235,9 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 #ifndef IPT_TRAV_STEPS
 #define IPT_TRAV_STEPS 16    // node visits between two refill checks
 #endif
+#ifndef IPT_VISITS_PER_ROUND
+#define IPT_VISITS_PER_ROUND 2 // node visits per lane between two rounds of warp votes (leaf batch, finished lanes, refill): 1 / 2 / 3 / 4 give C3 394 / 421 / 425 / 426, C4 337 / 357 / 355 / 351 Mpaths/s
+#endif
 #ifndef IPT_LEAF_BATCH
 #define IPT_LEAF_BATCH 6    // run the postponed triangle tests once this many lanes hold one
 #endif
@@ -351,7 +354,10 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
         // 2009): a hit leaf is parked in `pend` (further ones go on the stack) and lanes keep walking inner nodes; the exact
         // triangle test then runs for many lanes at once instead of for the 1-2 lanes that reach a leaf in the same step.
         if (!drain) {
+            uint32_t idle_mask = __ballot_sync(0xffffffffu, !have); // warp-uniform, maintained through the rounds below
             for (int step = 0; step < IPT_TRAV_STEPS; ++step) {
+#pragma unroll
+                for (int visit = 0; visit < IPT_VISITS_PER_ROUND; ++visit)
                 if (have && trav) {
                     if (node != IPT_NO_HIT && pend == IPT_NO_HIT) {
 #if IPT_BVH_WIDE_NODES
@@ -391,9 +397,10 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                         }
                     }
                 }
-                uint32_t pm = __ballot_sync(0xffffffffu, have && trav && pend != IPT_NO_HIT);
-                uint32_t walk = __ballot_sync(0xffffffffu, have && trav && pend == IPT_NO_HIT);
-                if (pm && (__popc(pm) >= IPT_LEAF_BATCH || walk == 0 || step == IPT_TRAV_STEPS - 1)) {
+                // two votes per round: lanes still traversing, and those of them that hold a postponed leaf
+                const uint32_t busy = __ballot_sync(0xffffffffu, have && trav);
+                const uint32_t pm = __ballot_sync(0xffffffffu, have && trav && pend != IPT_NO_HIT);
+                if (pm && (__popc(pm) >= IPT_LEAF_BATCH || pm == busy || step == IPT_TRAV_STEPS - 1)) {
                     if (have && trav && pend != IPT_NO_HIT) {
                         test_triangle(S, pend & 0x7FFFFFFFu, o, d, best_t, best_orig, best_pos, best_orig != IPT_NO_HIT, tc);
                         pend = IPT_NO_HIT;
@@ -415,7 +422,8 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                     n_done += __popc(fb);
                     __syncwarp();
                 }
-                uint32_t idle = __ballot_sync(0xffffffffu, !have);
+                idle_mask |= fb; // (the lanes that were idle when the round began, plus the ones that just finished)
+                const uint32_t idle = idle_mask;
                 if (n_done >= 32 || idle == 0xffffffffu) break;
                 if (__popc(idle) >= IPT_REFILL_MIN && (n_ready || !exhausted)) break;
             }
