@@ -77,6 +77,27 @@ def test_mesh_render_matches_oracle(lib, oracle):
     sc.close()
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 50])
+def test_tiny_meshes_render_like_the_oracle(n, lib, oracle):
+    """The persistent mesh kernel on degenerate trees (a lone triangle has no node at all, two triangles a single node): the
+    two-level tree per pixel against the oracle, and the last traced depth resolved in full (IPT_FLAG_RESOLVE_LAST_LEVEL:
+    every ray traced, not only the ones that reach a light) gives the same image as the shadow-ray shortcut."""
+    sd = capi.SceneDescription(f"mesh:{n}")
+    sc = capi.Scene(sd)
+    p = capi.default_params(width=48, height=48, pass_count=2, depth_max=2, schedule=[16, 8], flags=capi.FLAG_KEEP_ZERO_WEIGHT)
+    s, q, cnt, st = sc.render_host(p)
+    o = oracle.render(sd.ptr, p, oracle_lib.RNG_PHILOX, 0)
+    scale = max(o["sum"].max(), 1e-12)
+    assert np.array_equal(cnt.astype(np.uint64), o["counters"])
+    assert (np.abs(s - o["sum"]) / scale > 1e-5).mean() < 4e-3
+    assert abs(int(st.rays) - int(o["rays"])) <= 2e-4 * o["rays"] + 2
+    full = sc.render_host(capi.default_params(width=48, height=48, pass_count=2, depth_max=3, schedule=[8, 4, 2]))
+    resolved = sc.render_host(capi.default_params(width=48, height=48, pass_count=2, depth_max=3, schedule=[8, 4, 2], flags=capi.FLAG_RESOLVE_LAST_LEVEL))
+    assert np.allclose(full[0], resolved[0], rtol=2e-5, atol=1e-7) and full[3].rays == resolved[3].rays
+    assert full[3].light_hits == resolved[3].light_hits
+    sc.close()
+
+
 def test_c3_one_million_triangles_depth_8_with_common_random_numbers(lib, oracle):
     """BASELINE configs[2] (1 M triangles, depth 8, one child per hit) with the SAME Philox numbers on both sides: the mesh
     path traces every depth with the reference's exact arithmetic, so a pixel differs from the oracle only where an ulp of
