@@ -11,7 +11,7 @@
 namespace iptd {
 
 #ifndef IPT_STACK_SHORT
-#define IPT_STACK_SHORT 12  // entries per thread in shared memory
+#define IPT_STACK_SHORT 16  // entries per thread in shared memory (8 / 12 / 16 / 20 / 32: C4 343 / 359 / 365 / 350 / 319 Mpaths/s: beyond 16 the stacks eat into the L1 carve-out)
 #endif
 #define IPT_STACK_LOCAL (104 - IPT_STACK_SHORT)  // overflow entries in local memory (tree height bound 63 key bits + 32 index bits, + postponed leaves)
 #define IPT_BLOCK 256
