@@ -42,7 +42,7 @@ WORKLOADS = {
                text="procedural 1M-triangle random mesh inside the open box, max depth 8"),
     "c4": dict(config="configs[3]", scene="mesh:10000000", width=3840, height=2160, depth_max=8, schedule=[1] * 8, spp_total=4096, passes_per_step=4,
                text="10M-triangle synthetic mesh, sample-sharded across the GPUs"),
-    "c5": dict(config="configs[4]", scene="lightgrid:100x100", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], spp_total=16, passes_per_step=1,
+    "c5": dict(config="configs[4]", scene="lightgrid:100x100", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], spp_total=16, passes_per_step=16,
                tile=(768, 768, 512, 512), text="many-light CollectionLighting scene (10k emitters), 512x512 crop of the 2048x2048 frame per step"),
 }
 WORKLOAD = dict(WORKLOADS["c2"])

@@ -10,8 +10,8 @@ CONFIGS = {
     "c3": dict(scene="mesh:1000000", width=1920, height=1080, depth_max=8, schedule=[1] * 8, passes=16),
     "c3_tree": dict(scene="mesh:1000000", width=1920, height=1080, depth_max=4, schedule=[16, 8, 4, 2], passes=2),
     "c4": dict(scene="mesh:10000000", width=3840, height=2160, depth_max=8, schedule=[1] * 8, passes=4),
-    "c5_100": dict(scene="lightgrid:10x10", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], passes=1, tile=(768, 768, 512, 512)),
-    "c5": dict(scene="lightgrid:100x100", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], passes=1, tile=(768, 768, 512, 512)),
+    "c5_100": dict(scene="lightgrid:10x10", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], passes=16, tile=(768, 768, 512, 512)),
+    "c5": dict(scene="lightgrid:100x100", width=2048, height=2048, depth_max=4, schedule=[16, 8, 4, 2], passes=16, tile=(768, 768, 512, 512)),
 }
 sel = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c1", "c2", "c3", "c3_tree", "c5_100", "c5"]
 for name in sel:
