@@ -236,7 +236,7 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 #define IPT_TRAV_STEPS 16    // node visits between two refill checks
 #endif
 #ifndef IPT_VISITS_PER_ROUND
-#define IPT_VISITS_PER_ROUND 2 // node visits per lane between two rounds of warp votes (leaf batch, finished lanes, refill): 1 / 2 / 3 / 4 give C3 394 / 421 / 425 / 426, C4 337 / 357 / 355 / 351 Mpaths/s
+#define IPT_VISITS_PER_ROUND 3 // node visits per lane between two rounds of warp votes (finished lanes, waiting lanes, refill). With the pair queue: 1 / 2 / 3 / 4 give C3 436 / 459 / 464 / 410, C4 394 / 415 / 419 / 369 Mpaths/s
 #endif
 #ifndef IPT_LEAF_BATCH
 #define IPT_LEAF_BATCH 6    // run the postponed triangle tests once this many lanes hold one
@@ -245,10 +245,14 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 #ifndef IPT_MESH_MIN_BLOCKS
 #define IPT_MESH_MIN_BLOCKS 4
 #endif
+#ifndef IPT_PAIR_QUEUE
+#define IPT_PAIR_QUEUE 1 // 1: (owner lane, triangle) pairs are queued per warp and tested 32 at a time; 0: a lane tests its own postponed leaf
+#endif
 #define IPT_POOL 64 // entries per warp and pool: fewer than 32 wait when up to 32 more arrive
 // dynamic shared memory of k_extend_mesh: the short stacks, then per warp a READY pool (ray index, analytic hit distance,
 // analytic primitive) and a DONE pool (ray index, hit distance, primitive id, primitive id as queued)
-#define IPT_MESH_POOL_WORDS (7 * IPT_POOL)
+// + the pair queue: owner lane and triangle of 64 pairs, and per lane a 64-bit best key, the winner's sorted position, a count
+#define IPT_MESH_POOL_WORDS (7 * IPT_POOL + (IPT_PAIR_QUEUE ? 2 * IPT_POOL + 4 * 32 : 0))
 #define IPT_MESH_SMEM_BYTES ((IPT_STACK_SHORT * IPT_BLOCK + (IPT_BLOCK / 32) * IPT_MESH_POOL_WORDS) * sizeof(uint32_t))
 
 // SPEC (see SceneSpec in ipt_kernels.cuh): SPEC_BOX_SCENE = one inline area light, analytic part = grouped box planes +
@@ -259,9 +263,10 @@ __device__ __forceinline__ SurfHit trace_geometry(const DevScene& S, f3 o, f3 d,
 //   setup     32 rays are fetched from the queue together; every lane intersects the analytic primitives for its ray (at the
 //             last traced depth: the lights first — a ray that reaches none is finished) and parks (ray, analytic hit) in
 //             the warp's READY pool;
-//   traverse  a lane without a ray takes one from the READY pool and walks the LBVH (one node per step, triangle tests
-//             postponed and run for several lanes at once); a finished lane parks (ray, closest hit) in the DONE pool and
-//             takes the next ray at once;
+//   traverse  a lane without a ray takes one from the READY pool and walks the LBVH; a leaf it reaches is not tested by the
+//             lane but queued as an (owner lane, triangle) pair, and whenever 32 pairs wait the warp tests them together
+//             (IPT_PAIR_QUEUE: the exact triangle test at 32 lanes instead of the 6.5 that happened to hold a leaf); a
+//             finished lane parks (ray, closest hit) in the DONE pool and takes the next ray at once;
 //   finalise  whenever 32 results wait, the warp runs the light test / decision / emission / hit append of main.cpp:111-128
 //             for them.
 // Round 1's kernel ran setup and finalisation on the 4-8 lanes that happened to be idle or finished (profiles/tuning_r02.md:
@@ -277,6 +282,13 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
     uint32_t* rd_idx = pool;                 float* rd_at = reinterpret_cast<float*>(pool + IPT_POOL); uint32_t* rd_ap = pool + 2 * IPT_POOL;
     uint32_t* dn_idx = pool + 3 * IPT_POOL;  float* dn_t = reinterpret_cast<float*>(pool + 4 * IPT_POOL);
     uint32_t* dn_prim = pool + 5 * IPT_POOL; uint32_t* dn_iprim = pool + 6 * IPT_POOL;
+#if IPT_PAIR_QUEUE
+    uint32_t* pq_own = pool + 7 * IPT_POOL;  uint32_t* pq_tri = pool + 8 * IPT_POOL;
+    unsigned long long* bk = reinterpret_cast<unsigned long long*>(pool + 9 * IPT_POOL); // 32 x u64 (8-byte aligned: pool offsets are even)
+    uint32_t* bp = pool + 9 * IPT_POOL + 64;  uint32_t* dc = pool + 9 * IPT_POOL + 96;
+    uint32_t pq_n = 0;    // warp-uniform: pairs waiting
+    uint32_t pending = 0; // pairs of THIS lane's ray that wait in the queue
+#endif
     uint32_t n_ready = 0, n_done = 0; // warp-uniform
     bool exhausted = false;           // warp-uniform
     uint32_t n_surface = 0, n_light = 0, n_miss = 0, n_dropped = 0;
@@ -355,6 +367,102 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
         // triangle test then runs for many lanes at once instead of for the 1-2 lanes that reach a leaf in the same step.
         if (!drain) {
             uint32_t idle_mask = __ballot_sync(0xffffffffu, !have); // warp-uniform, maintained through the rounds below
+#if IPT_PAIR_QUEUE
+            // 32 queued (owner lane, triangle) pairs at a time: every lane fetches its pair's ray from the owner by shuffle, runs
+            // the exact triangle test and folds a hit into the owner's best (distance, original index) with a 64-bit
+            // shared-memory atomicMin — the tie-break of the linear scan (equal distance: lowest original index) is the order
+            // of those keys; a triangle must be STRICTLY nearer than the analytic winner, whose key carries index 0.
+            auto test_pairs = [&](uint32_t cnt) {
+                const unsigned long long key0 = ((unsigned long long)__float_as_uint(best_t) << 32) | (best_orig == IPT_NO_HIT ? 0u : best_orig);
+                bk[lane] = have ? key0 : ~0ull;
+                dc[lane] = 0;
+                __syncwarp();
+                const bool valid = lane < cnt;
+                const uint32_t e = pq_n - cnt + lane;
+                const uint32_t own = valid ? pq_own[e] : lane, pos = valid ? pq_tri[e] : 0u;
+                f3 po = mk3(__shfl_sync(0xffffffffu, o.x, own), __shfl_sync(0xffffffffu, o.y, own), __shfl_sync(0xffffffffu, o.z, own));
+                f3 pd = mk3(__shfl_sync(0xffffffffu, d.x, own), __shfl_sync(0xffffffffu, d.y, own), __shfl_sync(0xffffffffu, d.z, own));
+                unsigned long long key = ~0ull;
+                if (valid) {
+                    f8 r0 = ldg256(&S.tris[4 * (size_t)pos]);
+                    f8 r1 = ldg256(&S.tris[4 * (size_t)pos + 2]);
+                    ++tc.tris;
+                    f3 rel;
+                    float t = isect_parallelogram(mk3(r0.v[0], r0.v[1], r0.v[2]), mk3(r0.v[3], r0.v[4], r0.v[5]), mk3(r0.v[6], r0.v[7], r1.v[0]),
+                                                  mk3(r1.v[1], r1.v[2], r1.v[3]), true, po, pd, &rel);
+                    if (t != IPT_INF) {
+                        key = ((unsigned long long)__float_as_uint(t) << 32) | __float_as_uint(r1.v[4]);
+                        atomicMin(&bk[own], key);
+                    }
+                    atomicAdd(&dc[own], 1u);
+                }
+                __syncwarp();
+                if (key != ~0ull && bk[own] == key) bp[own] = pos; // the winner leaves its sorted position
+                __syncwarp();
+                const unsigned long long k = bk[lane];
+                if (have && k != key0) { best_t = __uint_as_float((uint32_t)(k >> 32)); best_orig = (uint32_t)k; best_pos = bp[lane]; }
+                pending -= dc[lane];
+                pq_n -= cnt;
+                __syncwarp();
+            };
+            auto queue_leaf = [&](uint32_t leaf) { // warp-wide: lanes with leaf != IPT_NO_HIT append (lane, sorted triangle position)
+                const uint32_t m = __ballot_sync(0xffffffffu, leaf != IPT_NO_HIT);
+                if (m) {
+                    if (leaf != IPT_NO_HIT) {
+                        const uint32_t k = pq_n + __popc(m & lt_mask);
+                        pq_own[k] = lane; pq_tri[k] = leaf;
+                        ++pending;
+                    }
+                    pq_n += __popc(m);
+                    __syncwarp();
+                    if (pq_n >= 32) test_pairs(32);
+                }
+            };
+            for (int step = 0; step < IPT_TRAV_STEPS; ++step) {
+#pragma unroll
+                for (int visit = 0; visit < IPT_VISITS_PER_ROUND; ++visit) {
+                    uint32_t leaf_a = IPT_NO_HIT, leaf_b = IPT_NO_HIT;
+                    if (have && trav && node != IPT_NO_HIT) {
+#if IPT_BVH_WIDE_NODES
+                        f8 n0 = ldg256(&S.nodes[node]);
+                        f8 n1 = ldg256(reinterpret_cast<const char*>(&S.nodes[node]) + 32);
+                        ++tc.nodes;
+                        uint32_t left = __float_as_uint(n0.v[3]), right = __float_as_uint(n0.v[7]);
+                        float tn0 = slab(n0.v[0], n0.v[1], n0.v[2], n0.v[4], n0.v[5], n0.v[6], R.c, R.inv, best_t);
+                        float tn1 = slab(n1.v[0], n1.v[1], n1.v[2], n1.v[4], n1.v[5], n1.v[6], R.c, R.inv, best_t);
+#else
+                        u8x32 q = ldg256u(&S.qnodes[node]);
+                        ++tc.nodes;
+                        uint32_t left = q.v[6], right = q.v[7];
+                        float tn0 = slab_q(q.v[0], q.v[1], q.v[2], R, best_t);
+                        float tn1 = slab_q(q.v[3], q.v[4], q.v[5], R, best_t);
+#endif
+                        bool h0 = tn0 != IPT_INF, h1 = tn1 != IPT_INF;
+                        if (h0 && (left & 0x80000000u)) { leaf_a = left & 0x7FFFFFFFu; h0 = false; }
+                        if (h1 && (right & 0x80000000u)) { leaf_b = right & 0x7FFFFFFFu; h1 = false; }
+                        uint32_t nxt = IPT_NO_HIT;
+                        if (h0 && h1) {
+                            bool first0 = tn0 <= tn1;
+                            nxt = first0 ? left : right;
+                            st.push(first0 ? right : left);
+                        } else if (h0) nxt = left;
+                        else if (h1) nxt = right;
+                        if (nxt == IPT_NO_HIT && st.n) nxt = st.pop(); // the stack holds inner nodes only
+                        node = nxt;
+                    }
+                    queue_leaf(leaf_a);
+                    queue_leaf(leaf_b);
+                }
+                // a lane whose walk is over waits for its queued pairs; they are tested when enough lanes wait, when nobody walks
+                // any more, and at the end of every block of rounds
+                {
+                    const uint32_t walking = __ballot_sync(0xffffffffu, have && trav && node != IPT_NO_HIT);
+                    const uint32_t waiting = __ballot_sync(0xffffffffu, have && trav && node == IPT_NO_HIT && pending != 0);
+                    if (pq_n && (walking == 0 || __popc(waiting) >= IPT_LEAF_BATCH || step == IPT_TRAV_STEPS - 1))
+                        while (pq_n) test_pairs(min(pq_n, 32u));
+                    if (have && trav && node == IPT_NO_HIT && pending == 0) trav = false;
+                }
+#else
             for (int step = 0; step < IPT_TRAV_STEPS; ++step) {
 #pragma unroll
                 for (int visit = 0; visit < IPT_VISITS_PER_ROUND; ++visit)
@@ -407,6 +515,7 @@ __global__ void __launch_bounds__(IPT_BLOCK, IPT_MESH_MIN_BLOCKS) k_extend_mesh(
                         if (node == IPT_NO_HIT && st.n == 0) trav = false;
                     }
                 }
+#endif
                 // finished lanes park their result and become idle
                 bool fin = have && !trav;
                 uint32_t fb = __ballot_sync(0xffffffffu, fin);
